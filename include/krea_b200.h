@@ -1,0 +1,107 @@
+/* krea_b200.h — C ABI of libkrea_b200.so (B200 / sm_100a kernels for the Self-Forcing
+ * causal-inference hot path of krea-ai/realtime-video).
+ *
+ * The reference has no FFI of its own (it is pure Python over torch), so this
+ * ABI is the boundary a maintainer binds with ctypes (INTEGRATION.md shows the stub).  Each
+ * entry point names the reference code it replaces (paths relative to the reference repo).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated; the caller (PyTorch) owns all memory,
+ *     kernels never allocate; `stream` is a cudaStream_t passed as void*.
+ *   - 16-bit tensors: dtype 0 = bfloat16, 1 = float16.  "ld*" = leading dimension in elements.
+ *   - return 0 on success, negative KR_ERR_* otherwise; kr_last_error() gives the message of
+ *     the calling thread's last failure.  Nothing throws across the ABI.
+ *   - calls are asynchronous on `stream`; re-entrant, but two calls must not touch the same
+ *     KV cache concurrently (the reference is single-threaded on GPU work,
+ *     release_server.py:918).
+ */
+#ifndef KREA_B200_H_
+#define KREA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KR_OK 0
+#define KR_ERR_INVALID_ARG (-1)
+#define KR_ERR_UNSUPPORTED_SHAPE (-2)
+#define KR_ERR_CUDA (-3)
+#define KR_ERR_NO_DEVICE (-4)
+#define KR_ERR_TENSORMAP (-5)
+
+/* library version (major*10000 + minor*100 + patch) and last error string */
+int kr_version(void);
+const char* kr_last_error(void);
+
+/* GEMM epilogues of kr_gemm */
+#define KR_EPI_BIAS 0          /* out = cast(acc + bias)                                         */
+#define KR_EPI_BIAS_GELU 1     /* out = cast(gelu_tanh(cast(acc + bias)))                        */
+#define KR_EPI_BIAS_GATE_RES 2 /* out = cast(res + cast(cast(acc+bias) * gate[row/rows_per_gate])) */
+#define KR_EPI_BIAS_RES 3      /* out = cast(res + cast(acc + bias))                             */
+#define KR_EPI_F32 4           /* out(fp32) = (acc + bias) * alpha                               */
+
+/* out[M,N] = epilogue(a[M,K] @ w[N,K]^T + bias[N]); tcgen05/TMEM tensor-core GEMM.
+ * Replaces nn.Linear (cuBLASLt) + the elementwise ops that follow it:
+ *   to_qkv / q / k / v / o      wan/modules/causal_model.py:246-253, :396
+ *   gate + residual             wan/modules/causal_model.py:476, :487-488
+ *   ffn.0 + GELU(tanh), ffn.2   wan/modules/causal_model.py:433-435
+ *   cross-attn q/k/v/o          wan/modules/model.py:183-190, :226-227
+ *   patch/text/time embeddings, time_projection, head   causal_model.py:874-902, :507-522
+ * Needs K % 64 == 0, N % 32 == 0, ld* % 8 == 0.  bias/residual/gate may be NULL when unused. */
+int kr_gemm(int dtype, int epilogue, const void* a, int lda, const void* w, int ldw,
+            const void* bias, void* out, int ldc, int M, int N, int K, const void* residual,
+            int ldr, const void* gate, int gate_stride, int rows_per_gate, float alpha,
+            void* stream);
+
+/* softmax(scale * q k^T) v, head_dim 128, [L, heads, 128] layout, bf16/fp16, fp32 softmax.
+ * mask_mode 0: none (cached self-attention causal_model.py:386-390, cross-attention
+ * model.py:214-215); mask_mode 1: block-causal rule of get_block_mask (causal_model.py:109-141)
+ * with block_len = frame_seqlen*num_frame_per_block tokens and window = local_attn_size *
+ * frame_seqlen tokens (0 = global).  Replaces flash_attn_func / flex_attention. */
+int kr_attn_fwd(int dtype, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
+                void* out, int ldo, int Lq, int Lkv, int heads, float softmax_scale, int mask_mode,
+                int block_len, int window, void* stream);
+
+/* WanLayerNorm (+affine) (+per-frame modulation x*(1+scale)+shift).
+ * mod: [frames, mod_rows, D] 16-bit or NULL; w,b: [D] or NULL.
+ * Replaces wan/modules/model.py:88-98 + causal_model.py:466-471, :482-485, :520-522 (bf16). */
+int kr_ln_modulate(const void* x, int ldx, void* out, int ldo, int rows, int D, float eps,
+                   const void* w, const void* b, const void* mod, int mod_rows, int shift_idx,
+                   int scale_idx, int rows_per_frame, void* stream);
+
+/* q,k: WanRMSNorm over D (model.py:69-85) then 3-axis RoPE (causal_model.py:143-171) written to
+ * q_out and to the K cache slot; v copied to the V cache slot (causal_model.py:378-385, :310-311).
+ * rope: float2 (cos,sin) [max_pos, head_dim/2] or NULL (no rotation, v may be NULL too). */
+int kr_qkv_norm_rope(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
+                     const void* wq, const void* wk, void* q_out, int ldqo, void* k_out, int ldko,
+                     void* v_out, int ldvo, const void* rope, int rows, int D, int head_dim,
+                     int grid_h, int grid_w, int start_frame, float eps, void* stream);
+
+/* WanRMSNorm rows (cross-attention q / k): model.py:69-85, :183-190 */
+int kr_rmsnorm(const void* x, int ldx, void* out, int ldo, const void* w, int rows, int D,
+               float eps, void* stream);
+
+/* e = modulation[mod_rows, D] + e0[frames, mod_rows, D]  (causal_model.py:466, :521) */
+int kr_add_modulation(const void* modulation, const void* e0, int lde0_frame, void* out,
+                      int frames, int mod_rows, int D, void* stream);
+
+/* elementwise activation on bf16: kind 0 = SiLU, 1 = GELU(tanh)  (causal_model.py:617-623) */
+int kr_activation(const void* x, void* y, size_t n, int kind, void* stream);
+
+/* Conv3d(k=s=(1,2,2)) patch embedding as im2col: x[C,F,H,W] (element strides sc,sf,sh,sw) ->
+ * tokens [F*(H/2)*(W/2), 4C]  (causal_model.py:614-615, :874-877) */
+int kr_patchify(const void* x, long sc, long sf, long sh, long sw, void* out, int C, int F, int H,
+                int W, void* stream);
+
+/* unpatchify (causal_model.py:1126-1149) fused with flow->x0 in fp64
+ * (utils/wan_wrapper.py:181-205): flow,x0,xt are [F,C,H,W]; sigma: double[F]; x0 may be NULL */
+int kr_unpatchify_x0(const void* head_out, int ldh, const void* xt, const double* sigma,
+                     void* flow, void* x0, int C, int F, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KREA_B200_H_ */

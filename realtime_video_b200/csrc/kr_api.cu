@@ -1,0 +1,107 @@
+// kr_api.cu — the extern "C" surface declared in include/krea_b200.h.
+#include "../../include/krea_b200.h"
+#include "kr_common.cuh"
+#include "kr_ops.h"
+
+
+#define KR_REQUIRE(cond, msg)                 \
+  do {                                        \
+    if (!(cond)) {                            \
+      kr::set_last_error("%s: %s", __func__, msg); \
+      return KR_ERR_INVALID_ARG;              \
+    }                                         \
+  } while (0)
+
+extern "C" {
+
+int kr_version(void) { return 100; }
+const char* kr_last_error(void) { return kr::last_error(); }
+
+int kr_gemm(int dtype, int epilogue, const void* a, int lda, const void* w, int ldw,
+            const void* bias, void* out, int ldc, int M, int N, int K, const void* residual,
+            int ldr, const void* gate, int gate_stride, int rows_per_gate, float alpha,
+            void* stream) {
+  KR_REQUIRE(a && w && out, "null a/w/out");
+  KR_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (bf16) or 1 (fp16)");
+  kr::GemmParams p;
+  p.out = out; p.bias = bias; p.residual = residual; p.gate = gate;
+  p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.ldr = ldr; p.gate_stride = gate_stride;
+  p.rows_per_gate = rows_per_gate; p.alpha = alpha;
+  return kr::gemm_tn(dtype, epilogue, a, lda, w, ldw, p, static_cast<cudaStream_t>(stream));
+}
+
+int kr_attn_fwd(int dtype, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
+                void* out, int ldo, int Lq, int Lkv, int heads, float softmax_scale, int mask_mode,
+                int block_len, int window, void* stream) {
+  KR_REQUIRE(q && k && v && out, "null q/k/v/out");
+  KR_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (bf16) or 1 (fp16)");
+  KR_REQUIRE(mask_mode == 0 || mask_mode == 1, "mask_mode must be 0 or 1");
+  kr::AttnParams p;
+  p.out = out; p.ldo = ldo; p.Lq = Lq; p.Lkv = Lkv; p.heads = heads;
+  p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  p.mask_mode = mask_mode; p.block_len = block_len; p.window = window;
+  return kr::attn_fwd(dtype, q, ldq, k, ldk, v, ldv, p, static_cast<cudaStream_t>(stream));
+}
+
+int kr_ln_modulate(const void* x, int ldx, void* out, int ldo, int rows, int D, float eps,
+                   const void* w, const void* b, const void* mod, int mod_rows, int shift_idx,
+                   int scale_idx, int rows_per_frame, void* stream) {
+  KR_REQUIRE(x && out, "null x/out");
+  return kr::ln_modulate(x, ldx, out, ldo, rows, D, eps, w, b, mod, mod_rows, shift_idx, scale_idx,
+                         rows_per_frame, static_cast<cudaStream_t>(stream));
+}
+
+int kr_qkv_norm_rope(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
+                     const void* wq, const void* wk, void* q_out, int ldqo, void* k_out, int ldko,
+                     void* v_out, int ldvo, const void* rope, int rows, int D, int head_dim,
+                     int grid_h, int grid_w, int start_frame, float eps, void* stream) {
+  KR_REQUIRE(q && k && wq && wk && q_out && k_out, "null q/k/weights/outputs");
+  KR_REQUIRE((v == nullptr) == (v_out == nullptr), "v and v_out must both be given or both null");
+  kr::QkvPostParams p;
+  p.q = static_cast<const uint16_t*>(q); p.k = static_cast<const uint16_t*>(k);
+  p.v = static_cast<const uint16_t*>(v);
+  p.ldq = ldq; p.ldk = ldk; p.ldv = ldv;
+  p.wq = static_cast<const uint16_t*>(wq); p.wk = static_cast<const uint16_t*>(wk);
+  p.q_out = static_cast<uint16_t*>(q_out); p.ldqo = ldqo;
+  p.k_out = static_cast<uint16_t*>(k_out); p.ldko = ldko;
+  p.v_out = static_cast<uint16_t*>(v_out); p.ldvo = ldvo;
+  p.rope = static_cast<const float2*>(rope);
+  p.D = D; p.head_dim = head_dim; p.grid_h = grid_h; p.grid_w = grid_w; p.start_frame = start_frame;
+  p.eps = eps;
+  return kr::qkv_post(p, rows, static_cast<cudaStream_t>(stream));
+}
+
+int kr_rmsnorm(const void* x, int ldx, void* out, int ldo, const void* w, int rows, int D,
+               float eps, void* stream) {
+  KR_REQUIRE(x && out && w, "null x/out/w");
+  return kr::rmsnorm_rows(x, ldx, out, ldo, w, rows, D, eps, static_cast<cudaStream_t>(stream));
+}
+
+int kr_add_modulation(const void* modulation, const void* e0, int lde0_frame, void* out,
+                      int frames, int mod_rows, int D, void* stream) {
+  KR_REQUIRE(modulation && e0 && out, "null pointer");
+  return kr::add_modulation(modulation, e0, lde0_frame, out, frames, mod_rows, D,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int kr_activation(const void* x, void* y, size_t n, int kind, void* stream) {
+  KR_REQUIRE(x && y, "null pointer");
+  KR_REQUIRE(kind == 0 || kind == 1, "kind must be 0 (silu) or 1 (gelu-tanh)");
+  return kr::activation(x, y, n, kind, static_cast<cudaStream_t>(stream));
+}
+
+int kr_patchify(const void* x, long sc, long sf, long sh, long sw, void* out, int C, int F, int H,
+                int W, void* stream) {
+  KR_REQUIRE(x && out, "null pointer");
+  return kr::patchify(x, sc, sf, sh, sw, out, C, F, H, W, static_cast<cudaStream_t>(stream));
+}
+
+int kr_unpatchify_x0(const void* head_out, int ldh, const void* xt, const double* sigma,
+                     void* flow, void* x0, int C, int F, int H, int W, void* stream) {
+  KR_REQUIRE(head_out && flow, "null pointer");
+  KR_REQUIRE(x0 == nullptr || (xt && sigma), "x0 requested without xt/sigma");
+  return kr::unpatchify_x0(head_out, ldh, xt, sigma, flow, x0, C, F, H, W,
+                           static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,392 @@
+// kr_attn.cu — tcgen05/TMEM flash-attention forward for sm_100a, head_dim 128.
+//
+//   O[q, h, :] = softmax_k( scale * Q[q, h, :] . K[k, h, :] ) V[k, h, :]
+//
+// Replaces flash_attn_func (FA2 mma.sync) on the reference path:
+//   * cached self-attention   wan/modules/causal_model.py:386-390 -> attention.py:65-70
+//   * recompute (block-causal) self-attention  causal_model.py:339-348 (FlexAttention)
+//     mask rule causal_model.py:134-138: allowed iff kv < ends[q] (| q == kv), optional window
+//   * T5 cross-attention      wan/modules/model.py:214-215
+// Layout is the reference's [L, heads, 128] (row pitch = heads*128 elements), K/V read in place
+// from the rolling cache tensors.
+//
+// CTA = 256 query rows of one head (two 128-row tiles, "ping-pong"): while softmax warpgroup 0
+// works on S0 the tensor core runs P1.V and Q1.K^T for warpgroup 1 and vice versa.
+//   warp 0        : TMA producer (Q once, K/V ring of 32 KB stages)
+//   warp 1        : tcgen05.mma issuer
+//   warps 4..7    : softmax warpgroup 0 (one thread per query row)
+//   warps 8..11   : softmax warpgroup 1
+// TMEM (512 cols): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P (16-bit) aliases the
+// first 64 columns of its S buffer and feeds the P.V MMA as the TMEM A operand.
+// Online softmax with lazy rescaling (O is only rescaled when the running max grows by > 2^8).
+#include "kr_common.cuh"
+#include "kr_ops.h"
+
+#include <cmath>
+
+namespace kr {
+
+
+static constexpr int kHeadDim = 128;
+static constexpr int kTileQ = 128;
+static constexpr int kTileKV = 128;
+static constexpr int kKvStages = 4;
+static constexpr int kTileBytes = kTileKV * kHeadDim * 2;   // 32 KB
+static constexpr int kHalfBytes = kTileBytes / 2;           // one 64-column swizzle panel
+static constexpr int kAttnThreads = 384;
+static constexpr int kAttnSmem = 2 * kTileBytes + kKvStages * kTileBytes + 1024 + 256;
+
+template <bool kBf16>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_q = smem;                          // 2 tiles
+  uint8_t* smem_kv = smem + 2 * kTileBytes;        // kKvStages tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + kKvStages * kTileBytes);
+  uint64_t* q_full = bars;                 // [1]
+  uint64_t* kv_full = bars + 1;            // [kKvStages]
+  uint64_t* kv_empty = kv_full + kKvStages;   // [kKvStages]
+  uint64_t* s_full = kv_empty + kKvStages;    // [2]
+  uint64_t* p_ready = s_full + 2;          // [2]
+  uint64_t* o_final = p_ready + 2;         // [1]
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_final + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int q0 = blockIdx.x * 2 * kTileQ;
+
+  // number of KV tiles this CTA visits
+  int kv_limit = p.Lkv;
+  if (p.mask_mode == 1) {
+    int last_q = q0 + 2 * kTileQ - 1;
+    if (last_q > p.Lq - 1) last_q = p.Lq - 1;
+    const int hi = (last_q / p.block_len + 1) * p.block_len;
+    if (hi < kv_limit) kv_limit = hi;
+  }
+  const int n_tiles = (kv_limit + kTileKV - 1) / kTileKV;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_k);
+    prefetch_tmap(&tmap_v);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int i = 0; i < kKvStages; ++i) {
+        mbar_init(&kv_full[i], 1);
+        mbar_init(&kv_empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s_full[i], 1);
+        mbar_init(&p_ready[i], 128);
+      }
+      mbar_init(o_final, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_base_smem);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int col = head * kHeadDim;
+      mbar_expect_tx(q_full, 2 * kTileBytes);
+      for (int t = 0; t < 2; ++t)
+        for (int h = 0; h < 2; ++h)
+          tma_load_2d(smem_q + t * kTileBytes + h * kHalfBytes, &tmap_q, q_full, col + h * 64,
+                      q0 + t * kTileQ);
+      int stage = 0;
+      uint32_t phase = 0;
+      // ring order: K0 V0 K1 V1 ...
+      for (int it = 0; it < 2 * n_tiles; ++it) {
+        const int j = it >> 1;
+        const CUtensorMap* tm = (it & 1) ? &tmap_v : &tmap_k;
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_expect_tx(&kv_full[stage], kTileBytes);
+        for (int h = 0; h < 2; ++h)
+          tma_load_2d(smem_kv + stage * kTileBytes + h * kHalfBytes, tm, &kv_full[stage],
+                      col + h * 64, j * kTileKV);
+        if (++stage == kKvStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_qk = make_idesc<kBf16>(128, 128, 0, 0);   // A,B K-major
+    constexpr uint32_t idesc_pv = make_idesc<kBf16>(128, 128, 0, 1);   // B (=V) MN-major
+    const uint32_t q_addr = smem_u32(smem_q);
+    const uint32_t kv_addr = smem_u32(smem_kv);
+    const uint32_t tS[2] = {tmem_base + 0, tmem_base + 128};
+    const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
+
+    auto issue_qk = [&](int wg, int stage) {
+      const uint32_t a = q_addr + wg * kTileBytes;
+      const uint32_t b = kv_addr + stage * kTileBytes;
+#pragma unroll
+      for (int k = 0; k < kHeadDim / 16; ++k) {
+        const uint32_t off = (k >> 2) * kHalfBytes + (k & 3) * 32;
+        umma_ss(tS[wg], make_smem_desc(a + off, 16, 1024), make_smem_desc(b + off, 16, 1024),
+                idesc_qk, k != 0 ? 1u : 0u);
+      }
+    };
+    auto issue_pv = [&](int wg, int stage, bool first) {
+      const uint32_t b = kv_addr + stage * kTileBytes;
+#pragma unroll
+      for (int k = 0; k < kTileKV / 16; ++k) {
+        // P: 16 keys = 8 TMEM columns per k-step; V: 16 key rows of 128 B per panel
+        umma_ts(tO[wg], tS[wg] + k * 8, make_smem_desc(b + k * 2048, kHalfBytes, 1024), idesc_pv,
+                (first && k == 0) ? 0u : 1u);
+      }
+    };
+
+    int stage = 0;
+    uint32_t phase = 0;
+    auto advance = [&]() {
+      if (++stage == kKvStages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    };
+
+    mbar_wait(q_full, 0);
+    // prologue: S0 = Q0 K0^T, S1 = Q1 K0^T
+    mbar_wait(&kv_full[stage], phase);
+    tc_fence_after();
+    if (lane == 0) {
+      issue_qk(0, stage);
+      umma_commit(&s_full[0]);
+      issue_qk(1, stage);
+      umma_commit(&s_full[1]);
+      umma_commit(&kv_empty[stage]);
+    }
+    __syncwarp();
+    advance();
+    for (int j = 0; j < n_tiles; ++j) {
+      const int v_stage = stage;
+      mbar_wait(&kv_full[v_stage], phase);   // V_j
+      advance();
+      const int k_stage = stage;
+      const bool more = (j + 1 < n_tiles);
+      // ---- warpgroup 0 ----
+      mbar_wait(&p_ready[0], j & 1);
+      tc_fence_after();
+      if (lane == 0) issue_pv(0, v_stage, j == 0);
+      __syncwarp();
+      if (more) {
+        mbar_wait(&kv_full[k_stage], phase);   // K_{j+1}
+        tc_fence_after();
+        if (lane == 0) {
+          issue_qk(0, k_stage);
+          umma_commit(&s_full[0]);
+        }
+        __syncwarp();
+      }
+      // ---- warpgroup 1 ----
+      mbar_wait(&p_ready[1], j & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        issue_pv(1, v_stage, j == 0);
+        umma_commit(&kv_empty[v_stage]);
+        if (more) {
+          issue_qk(1, k_stage);
+          umma_commit(&s_full[1]);
+          umma_commit(&kv_empty[k_stage]);
+        }
+      }
+      __syncwarp();
+      if (more) advance();
+    }
+    if (lane == 0) umma_commit(o_final);
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== softmax warpgroups =====================
+    const int wg = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    const int q_row = q0 + wg * kTileQ + row_in_tile;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + wg * 128;
+    const uint32_t tO = tmem_base + lane_off + 256 + wg * 128;
+
+    int row_hi = p.Lkv, row_lo = 0;
+    if (p.mask_mode == 1) {
+      const int qq = q_row < p.Lq ? q_row : p.Lq - 1;
+      const int hi = (qq / p.block_len + 1) * p.block_len;
+      if (p.window > 0) row_lo = hi - p.window > 0 ? hi - p.window : 0;
+      if (hi < row_hi) row_hi = hi;
+    }
+
+    float m_run = -INFINITY;
+    float l_run = 0.f;
+    const float sl2 = p.scale_log2;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&s_full[wg], j & 1);
+      tc_fence_after();
+      uint32_t r0[32], r1[32], r2[32], r3[32];
+      tmem_ld_x32(tS + 0, r0);
+      tmem_ld_x32(tS + 32, r1);
+      tmem_ld_x32(tS + 64, r2);
+      tmem_ld_x32(tS + 96, r3);
+      tmem_ld_wait();
+
+      const int hi = row_hi - j * kTileKV;
+      const int lo = row_lo - j * kTileKV;
+      if (hi < kTileKV || lo > 0) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if (c >= hi || c < lo) r0[c] = 0xff800000u;
+          if (c + 32 >= hi || c + 32 < lo) r1[c] = 0xff800000u;
+          if (c + 64 >= hi || c + 64 < lo) r2[c] = 0xff800000u;
+          if (c + 96 >= hi || c + 96 < lo) r3[c] = 0xff800000u;
+        }
+      }
+      float mt = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        mt = fmaxf(mt, fmaxf(fmaxf(__uint_as_float(r0[c]), __uint_as_float(r1[c])),
+                             fmaxf(__uint_as_float(r2[c]), __uint_as_float(r3[c]))));
+      }
+      const float m_new = fmaxf(m_run, mt);
+      const bool need = (m_new - m_run) * sl2 > 8.0f;   // also true when m_run == -inf
+      const float m_used = need ? m_new : m_run;
+      const float alpha = need ? fast_exp2((m_run - m_new) * sl2) : 1.0f;
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        // rescale this row's O accumulator in TMEM
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[32];
+          tmem_ld_x32(tO + c * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_x32(tO + c * 32, o);
+        }
+      }
+      l_run *= alpha;
+      m_run = m_used;
+      // a row whose every visible key so far is masked (local window) keeps m = -inf: use 0
+      const float nms = (m_used == -INFINITY) ? 0.f : -m_used * sl2;
+      float rowsum = 0.f;
+      uint32_t pk[64];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        float a0 = fast_exp2(fmaf(__uint_as_float(r0[2 * c]), sl2, nms));
+        float a1 = fast_exp2(fmaf(__uint_as_float(r0[2 * c + 1]), sl2, nms));
+        float b0 = fast_exp2(fmaf(__uint_as_float(r1[2 * c]), sl2, nms));
+        float b1 = fast_exp2(fmaf(__uint_as_float(r1[2 * c + 1]), sl2, nms));
+        float c0 = fast_exp2(fmaf(__uint_as_float(r2[2 * c]), sl2, nms));
+        float c1 = fast_exp2(fmaf(__uint_as_float(r2[2 * c + 1]), sl2, nms));
+        float d0 = fast_exp2(fmaf(__uint_as_float(r3[2 * c]), sl2, nms));
+        float d1 = fast_exp2(fmaf(__uint_as_float(r3[2 * c + 1]), sl2, nms));
+        rowsum += (a0 + a1) + (b0 + b1) + (c0 + c1) + (d0 + d1);
+        pk[c] = kBf16 ? pack_bf16x2(a0, a1) : pack_f16x2(a0, a1);
+        pk[16 + c] = kBf16 ? pack_bf16x2(b0, b1) : pack_f16x2(b0, b1);
+        pk[32 + c] = kBf16 ? pack_bf16x2(c0, c1) : pack_f16x2(c0, c1);
+        pk[48 + c] = kBf16 ? pack_bf16x2(d0, d1) : pack_f16x2(d0, d1);
+      }
+      l_run += rowsum;
+      tmem_st_x32(tS + 0, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
+      tmem_st_x32(tS + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_ready[wg]);
+    }
+
+    // ---- epilogue: O / l -> global ----
+    mbar_wait(o_final, 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const bool row_ok = q_row < p.Lq;
+    uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + static_cast<size_t>(row_ok ? q_row : 0) * p.ldo +
+                     head * kHeadDim;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t o[32];
+      tmem_ld_x32(tO + c * 32, o);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 w;
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[q * 8 + i]) * inv_l;
+          if (kBf16) {
+            w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]);
+            w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
+          } else {
+            w.x = pack_f16x2(f[0], f[1]); w.y = pack_f16x2(f[2], f[3]);
+            w.z = pack_f16x2(f[4], f[5]); w.w = pack_f16x2(f[6], f[7]);
+          }
+          *reinterpret_cast<uint4*>(orow + c * 32 + q * 8) = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// q: [Lq, ldq] (head h at columns h*128..), k/v: [>=Lkv, ldk/ldv]; dtype 0 = bf16, 1 = fp16
+int attn_fwd(int dtype, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
+             const AttnParams& p, cudaStream_t stream) {
+  if (p.Lq <= 0 || p.Lkv <= 0 || p.heads <= 0) {
+    set_last_error("attn_fwd: non-positive shape Lq=%d Lkv=%d heads=%d", p.Lq, p.Lkv, p.heads);
+    return KR_ERR_INVALID_ARG;
+  }
+  if (ldq % 8 != 0 || ldk % 8 != 0 || ldv % 8 != 0 || p.ldo % 8 != 0) {
+    set_last_error("attn_fwd: leading dimensions must be multiples of 8 elements");
+    return KR_ERR_UNSUPPORTED_SHAPE;
+  }
+  if (p.mask_mode == 1 && p.block_len <= 0) {
+    set_last_error("attn_fwd: block-causal mask needs block_len > 0");
+    return KR_ERR_INVALID_ARG;
+  }
+  const bool bf = dtype == 0;
+  CUtensorMap tq, tk, tv;
+  int rc = make_tmap_2d(&tq, q, p.Lq, static_cast<uint64_t>(p.heads) * kHeadDim, ldq, kTileQ, 64, bf);
+  if (rc != KR_OK) return rc;
+  rc = make_tmap_2d(&tk, k, p.Lkv, static_cast<uint64_t>(p.heads) * kHeadDim, ldk, kTileKV, 64, bf);
+  if (rc != KR_OK) return rc;
+  rc = make_tmap_2d(&tv, v, p.Lkv, static_cast<uint64_t>(p.heads) * kHeadDim, ldv, kTileKV, 64, bf);
+  if (rc != KR_OK) return rc;
+  auto kern = bf ? attn_fwd_kernel<true> : attn_fwd_kernel<false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[bf ? 0 : 1]) {
+    cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e != cudaSuccess) {
+      set_last_error("attn_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return KR_ERR_CUDA;
+    }
+    attr_set[bf ? 0 : 1] = true;
+  }
+  dim3 grid((p.Lq + 2 * kTileQ - 1) / (2 * kTileQ), p.heads);
+  kern<<<grid, kAttnThreads, kAttnSmem, stream>>>(tq, tk, tv, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("attn_fwd: launch failed: %s", cudaGetErrorString(e));
+    return KR_ERR_CUDA;
+  }
+  return KR_OK;
+}
+
+}  // namespace kr

@@ -1,0 +1,388 @@
+// kr_gemm.cu — persistent tcgen05/TMEM GEMM for sm_100a.
+//
+//   C[M,N] = epilogue( A[M,K] @ W[N,K]^T + bias[N] )
+//
+// A and W are row-major with K contiguous (nn.Linear weight layout), 16-bit
+// (bf16 or fp16), accumulation in fp32 in tensor memory.
+//
+// Replaces, on the reference path, every cuBLASLt call issued by nn.Linear in the
+// DiT block (wan/modules/causal_model.py:246 to_qkv, :396 o, :433-435 ffn;
+// wan/modules/model.py:183-227 cross-attn q/k/v/o; causal_model.py:614-623
+// patch/text/time embeddings; :507 head) together with the elementwise kernels
+// that follow them (bias add, GELU-tanh, per-frame gate, residual add).
+//
+// Structure (one CTA per SM, persistent over output tiles):
+//   warp 0      : TMA producer  (A tile 128x64, W tile BLOCK_Nx64, SWIZZLE_128B)
+//   warp 1      : tcgen05.mma issuer (single elected lane), TMEM allocator
+//   warps 2..5  : epilogue (tcgen05.ld -> registers -> fused math -> global)
+// Pipelines: smem full/empty ring (kStages), TMEM accumulator double buffer
+// (2 x BLOCK_N fp32 columns) so the epilogue of tile i overlaps the mainloop of
+// tile i+1.
+#include "kr_common.cuh"
+#include "kr_ops.h"
+
+namespace kr {
+
+
+static constexpr int BLOCK_M = 128;
+static constexpr int BLOCK_K = 64;   // 64 x 16-bit = 128 B = one swizzle row
+static constexpr int UMMA_K = 16;
+static constexpr int kNumThreads = 192;
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N, bool kBf16, int kEpi>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024 B alignment for SWIZZLE_128B tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                       // [kStages]
+  uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;            // [2]
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_n = p.N / BLOCK_N;
+  const int num_tiles = num_m * num_n;
+  const int num_k = p.K / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < Cfg::kStages; ++i) {
+        mbar_init(&full_bar[i], 1);
+        mbar_init(&empty_bar[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tmem_full[i], 1);
+        mbar_init(&tmem_empty[i], 4);   // one arrive per epilogue warp
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::kTmemCols>(tmem_base_smem);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % num_m;
+        const int n_blk = tile / num_m;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * BLOCK_K,
+                      m_blk * BLOCK_M);
+          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * BLOCK_K,
+                      n_blk * BLOCK_N);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc<kBf16>(BLOCK_M, BLOCK_N, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t a_desc = make_smem_desc(a_addr + k * UMMA_K * 2, 16, 1024);
+            const uint64_t b_desc = make_smem_desc(b_addr + k * UMMA_K * 2, 16, 1024);
+            umma_ss(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
+          if (kb == num_k - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quarter = warp & 3;   // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % num_m;
+      const int n_blk = tile / num_m;
+      const int row = m_blk * BLOCK_M + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+
+      const uint16_t* gate_row = nullptr;
+      if constexpr (kEpi == EPI_BIAS_GATE_RES) {
+        const int g = row_ok ? row / p.rows_per_gate : 0;
+        gate_row = reinterpret_cast<const uint16_t*>(p.gate) + static_cast<size_t>(g) * p.gate_stride;
+      }
+
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n_blk * BLOCK_N + c * 32;
+        if (c == BLOCK_N / 32 - 1) {
+          // all TMEM reads of this accumulator done -> hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        if (row_ok) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+            const uint4* b4 = reinterpret_cast<const uint4*>(
+                reinterpret_cast<const uint16_t*>(p.bias) + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 bb = __ldg(b4 + q);
+              uint32_t w[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                float2 f = kBf16 ? unpack_bf16x2(w[h]) : unpack_f16x2(w[h]);
+                v[q * 8 + h * 2] += f.x;
+                v[q * 8 + h * 2 + 1] += f.y;
+              }
+            }
+          }
+          if constexpr (kEpi == EPI_F32) {
+            float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldc + col0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 f4 = make_float4(v[q * 4] * p.alpha, v[q * 4 + 1] * p.alpha,
+                                      v[q * 4 + 2] * p.alpha, v[q * 4 + 3] * p.alpha);
+              reinterpret_cast<float4*>(o)[q] = f4;
+            }
+          } else {
+            auto rnd = [](float x) -> float {
+              return kBf16 ? __bfloat162float(__float2bfloat16_rn(x))
+                           : __half2float(__float2half_rn(x));
+            };
+            if constexpr (kEpi == EPI_BIAS_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(rnd(v[j]));
+            }
+            if constexpr (kEpi == EPI_BIAS_GATE_RES) {
+              const uint4* g4 = reinterpret_cast<const uint4*>(gate_row + col0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 gg = __ldg(g4 + q);
+                uint32_t w[4] = {gg.x, gg.y, gg.z, gg.w};
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  float2 f = kBf16 ? unpack_bf16x2(w[h]) : unpack_f16x2(w[h]);
+                  v[q * 8 + h * 2] = rnd(rnd(v[q * 8 + h * 2]) * f.x);
+                  v[q * 8 + h * 2 + 1] = rnd(rnd(v[q * 8 + h * 2 + 1]) * f.y);
+                }
+              }
+            }
+            if constexpr (kEpi == EPI_BIAS_GATE_RES || kEpi == EPI_BIAS_RES) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(
+                  reinterpret_cast<const uint16_t*>(p.residual) + static_cast<size_t>(row) * p.ldr +
+                  col0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 rr = r4[q];
+                uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  float2 f = kBf16 ? unpack_bf16x2(w[h]) : unpack_f16x2(w[h]);
+                  if constexpr (kEpi == EPI_BIAS_RES) {
+                    v[q * 8 + h * 2] = f.x + rnd(v[q * 8 + h * 2]);
+                    v[q * 8 + h * 2 + 1] = f.y + rnd(v[q * 8 + h * 2 + 1]);
+                  } else {
+                    v[q * 8 + h * 2] = f.x + v[q * 8 + h * 2];
+                    v[q * 8 + h * 2 + 1] = f.y + v[q * 8 + h * 2 + 1];
+                  }
+                }
+              }
+            }
+            uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + static_cast<size_t>(row) * p.ldc + col0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 w;
+              if (kBf16) {
+                w.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                w.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                w.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                w.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+              } else {
+                w.x = pack_f16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                w.y = pack_f16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                w.z = pack_f16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                w.w = pack_f16x2(v[q * 8 + 6], v[q * 8 + 7]);
+              }
+              reinterpret_cast<uint4*>(o)[q] = w;
+            }
+          }
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host launcher
+// ---------------------------------------------------------------------------
+template <int BLOCK_N, bool kBf16, int kEpi>
+static int launch_gemm(const void* a, int lda, const void* w, int ldw, const GemmParams& p,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d(&ta, a, p.M, p.K, lda, BLOCK_M, BLOCK_K, kBf16);
+  if (rc != KR_OK) return rc;
+  rc = make_tmap_2d(&tb, w, p.N, p.K, ldw, BLOCK_N, BLOCK_K, kBf16);
+  if (rc != KR_OK) return rc;
+  auto kern = gemm_tn_kernel<BLOCK_N, kBf16, kEpi>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_last_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return KR_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int num_tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * (p.N / BLOCK_N);
+  int grid = sm_count();
+  if (grid > num_tiles) grid = num_tiles;
+  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("gemm: launch failed: %s", cudaGetErrorString(e));
+    return KR_ERR_CUDA;
+  }
+  return KR_OK;
+}
+
+template <int BLOCK_N, bool kBf16>
+static int dispatch_epi(int epi, const void* a, int lda, const void* w, int ldw,
+                        const GemmParams& p, cudaStream_t s) {
+  switch (epi) {
+    case EPI_BIAS: return launch_gemm<BLOCK_N, kBf16, EPI_BIAS>(a, lda, w, ldw, p, s);
+    case EPI_BIAS_GELU: return launch_gemm<BLOCK_N, kBf16, EPI_BIAS_GELU>(a, lda, w, ldw, p, s);
+    case EPI_BIAS_GATE_RES:
+      return launch_gemm<BLOCK_N, kBf16, EPI_BIAS_GATE_RES>(a, lda, w, ldw, p, s);
+    case EPI_BIAS_RES: return launch_gemm<BLOCK_N, kBf16, EPI_BIAS_RES>(a, lda, w, ldw, p, s);
+    case EPI_F32: return launch_gemm<BLOCK_N, kBf16, EPI_F32>(a, lda, w, ldw, p, s);
+    default: set_last_error("gemm: unknown epilogue %d", epi); return KR_ERR_INVALID_ARG;
+  }
+}
+
+// dtype: 0 = bf16, 1 = fp16
+int gemm_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, const GemmParams& p,
+            cudaStream_t stream) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) {
+    set_last_error("gemm: non-positive shape M=%d N=%d K=%d", p.M, p.N, p.K);
+    return KR_ERR_INVALID_ARG;
+  }
+  if (p.K % BLOCK_K != 0 || p.N % 32 != 0 || lda % 8 != 0 || ldw % 8 != 0 || p.ldc % 8 != 0) {
+    set_last_error("gemm: unsupported shape M=%d N=%d K=%d (need K%%64==0, N%%32==0, ld%%8==0)",
+                   p.M, p.N, p.K);
+    return KR_ERR_UNSUPPORTED_SHAPE;
+  }
+  if ((epi == EPI_BIAS_GATE_RES || epi == EPI_BIAS_RES) && p.residual == nullptr) {
+    set_last_error("gemm: residual epilogue without residual pointer");
+    return KR_ERR_INVALID_ARG;
+  }
+  if (epi == EPI_BIAS_GATE_RES && (p.gate == nullptr || p.rows_per_gate <= 0)) {
+    set_last_error("gemm: gate epilogue without gate pointer / rows_per_gate");
+    return KR_ERR_INVALID_ARG;
+  }
+  int bn;
+  if (p.N % 256 == 0) bn = 256;
+  else if (p.N % 128 == 0) bn = 128;
+  else if (p.N % 64 == 0) bn = 64;
+  else if (p.N % 32 == 0) bn = 32;
+  else bn = 0;
+  // prefer the tile width that fills the machine: small problems use narrower tiles
+  const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  if (bn == 256 && num_m * (p.N / 256) < sm_count() && p.N % 128 == 0) bn = 128;
+  if (bn == 128 && num_m * (p.N / 128) < sm_count() && p.N % 64 == 0) bn = 64;
+  const bool bf = dtype == 0;
+  switch (bn) {
+    case 256:
+      return bf ? dispatch_epi<256, true>(epi, a, lda, w, ldw, p, stream)
+                : dispatch_epi<256, false>(epi, a, lda, w, ldw, p, stream);
+    case 128:
+      return bf ? dispatch_epi<128, true>(epi, a, lda, w, ldw, p, stream)
+                : dispatch_epi<128, false>(epi, a, lda, w, ldw, p, stream);
+    case 64:
+      return bf ? dispatch_epi<64, true>(epi, a, lda, w, ldw, p, stream)
+                : dispatch_epi<64, false>(epi, a, lda, w, ldw, p, stream);
+    case 32:
+      return bf ? dispatch_epi<32, true>(epi, a, lda, w, ldw, p, stream)
+                : dispatch_epi<32, false>(epi, a, lda, w, ldw, p, stream);
+    default:
+      set_last_error("gemm: N=%d not a multiple of 32", p.N);
+      return KR_ERR_UNSUPPORTED_SHAPE;
+  }
+}
+
+}  // namespace kr

@@ -1,0 +1,73 @@
+// kr_ops.h — internal C++ interface between the kernels' host launchers and kr_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace kr {
+const char* last_error();
+
+enum GemmEpilogue : int {
+  EPI_BIAS = 0,           // out = cast(acc + bias)
+  EPI_BIAS_GELU = 1,      // out = cast(gelu_tanh(cast(acc + bias)))
+  EPI_BIAS_GATE_RES = 2,  // out = cast(res + cast(cast(acc + bias) * gate[row / rows_per_gate]))
+  EPI_BIAS_RES = 3,       // out = cast(res + cast(acc + bias))
+  EPI_F32 = 4,            // out(fp32) = (acc + bias) * alpha
+};
+
+struct GemmParams {
+  void* out;
+  const void* bias;      // [N] 16-bit or nullptr
+  const void* residual;  // [M, ldr] 16-bit (EPI_*_RES)
+  const void* gate;      // [G, gate_stride] 16-bit (EPI_BIAS_GATE_RES)
+  int M, N, K;
+  int ldc;               // elements
+  int ldr;               // elements
+  int gate_stride;       // elements between consecutive gate rows
+  int rows_per_gate;     // consecutive output rows sharing one gate row
+  float alpha;
+};
+int gemm_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, const GemmParams& p,
+            cudaStream_t stream);
+
+struct AttnParams {
+  void* out;           // [Lq, heads*128] 16-bit
+  int ldo;             // elements
+  int Lq, Lkv, heads;
+  float scale_log2;    // softmax_scale * log2(e)
+  // mask: 0 none; 1 block-causal: key k visible to query q iff lo(q) <= k < hi(q),
+  //   hi(q) = min(Lkv, (q / block_len + 1) * block_len), lo(q) = window>0 ? max(0, hi'(q)-window) : 0
+  int mask_mode;
+  int block_len;       // tokens per causal block (frame_len * frames_per_block)
+  int window;          // tokens (local_attn_size * frame_len) or 0
+};
+int attn_fwd(int dtype, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
+             const AttnParams& p, cudaStream_t stream);
+
+int ln_modulate(const void* x, int ldx, void* out, int ldo, int rows, int D, float eps,
+                const void* w, const void* b, const void* mod, int mod_rows, int shift_idx,
+                int scale_idx, int rows_per_frame, cudaStream_t stream);
+
+struct QkvPostParams {
+  const uint16_t* q; const uint16_t* k; const uint16_t* v;
+  int ldq, ldk, ldv;
+  const uint16_t* wq; const uint16_t* wk;   // RMSNorm weights [D]
+  uint16_t* q_out; int ldqo;                // [rows, D]
+  uint16_t* k_out; int ldko;                // cache slot base (already offset to first row)
+  uint16_t* v_out; int ldvo;
+  const float2* rope;                       // may be null -> no rotation
+  int D, head_dim;
+  int grid_h, grid_w, start_frame;
+  float eps;
+};
+int qkv_post(const QkvPostParams& p, int rows, cudaStream_t stream);
+int rmsnorm_rows(const void* x, int ldx, void* out, int ldo, const void* w, int rows, int D,
+                 float eps, cudaStream_t stream);
+int add_modulation(const void* modulation, const void* e0, int lde0_frame, void* out, int frames,
+                   int mod_rows, int D, cudaStream_t stream);
+int activation(const void* x, void* y, size_t n, int kind, cudaStream_t stream);
+int patchify(const void* x, long sc, long sf, long sh, long sw, void* out, int C, int F, int H,
+             int W, cudaStream_t stream);
+int unpatchify_x0(const void* head_out, int ldh, const void* xt, const double* sigma, void* flow,
+                  void* x0, int C, int F, int H, int W, cudaStream_t stream);
+}  // namespace kr

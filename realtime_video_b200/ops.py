@@ -1,0 +1,245 @@
+"""Tensor-level wrappers over the C ABI (``include/krea_b200.h``).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every op below is
+one call into libkrea_b200.so.  All ops require CUDA tensors and raise otherwise — there is
+no eager / CPU fallback on the product path.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES, EPI_BIAS_RES, EPI_F32 = 0, 1, 2, 3, 4
+
+_DT = {torch.bfloat16: 0, torch.float16: 1}
+
+# count of kernels launched through this module (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def _count(n: int = 1) -> None:
+    global launch_count
+    launch_count += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, name: str, dtype=None) -> None:
+    if not t.is_cuda:
+        raise _lib.KreaB200Error(f"{name} must be a CUDA tensor (no CPU fallback in the product path)")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.KreaB200Error(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def _rows2d(t: torch.Tensor, name: str):
+    """View a [..., D] tensor with contiguous last dim and uniform row pitch as (rows, ld)."""
+    if t.stride(-1) != 1:
+        raise _lib.KreaB200Error(f"{name}: last dimension must be contiguous")
+    if t.dim() == 1:
+        return 1, t.shape[0]
+    if t.dim() == 2:
+        return t.shape[0], t.stride(0)
+    lead = t.shape[:-1]
+    ld = t.stride(-2)
+    # leading dims must collapse onto one pitch
+    exp = ld
+    for size, stride in zip(reversed(lead), reversed(t.stride()[:-1])):
+        if size != 1 and stride != exp:
+            raise _lib.KreaB200Error(f"{name}: rows are not uniformly strided {t.shape} {t.stride()}")
+        exp *= size
+    return math.prod(lead), ld
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+         epilogue: int = EPI_BIAS, out: Optional[torch.Tensor] = None,
+         residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
+         rows_per_gate: int = 0, alpha: float = 1.0) -> torch.Tensor:
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T + bias).  gate: [G, N] rows (pitch = stride(0))."""
+    _req(a, "a"); _req(w, "w", a.dtype)
+    M, lda = _rows2d(a, "a")
+    K = a.shape[-1]
+    N = w.shape[0]
+    if w.shape[1] != K or w.stride(1) != 1:
+        raise _lib.KreaB200Error(f"gemm: weight shape {tuple(w.shape)} does not match K={K}")
+    if out is None:
+        odt = torch.float32 if epilogue == EPI_F32 else a.dtype
+        out = torch.empty(*a.shape[:-1], N, dtype=odt, device=a.device)
+    _, ldc = _rows2d(out, "out")
+    ldr = 0
+    if residual is not None:
+        _req(residual, "residual", a.dtype)
+        _, ldr = _rows2d(residual, "residual")
+    gs = 0
+    if gate is not None:
+        _req(gate, "gate", a.dtype)
+        gs = gate.stride(0) if gate.dim() >= 2 else 0
+    lib = _lib.load()
+    rc = lib.kr_gemm(_DT[a.dtype], epilogue, a.data_ptr(), lda, w.data_ptr(), w.stride(0),
+                     _ptr(bias), out.data_ptr(), ldc, M, N, K, _ptr(residual), ldr, _ptr(gate), gs,
+                     rows_per_gate, alpha, _stream())
+    _lib.check(rc, "kr_gemm")
+    _count()
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, heads: int,
+              out: Optional[torch.Tensor] = None, softmax_scale: Optional[float] = None,
+              block_len: int = 0, window: int = 0) -> torch.Tensor:
+    """q [Lq, heads*128], k/v [Lkv, heads*128] (row pitch free) -> [Lq, heads*128].
+
+    block_len > 0 selects the block-causal mask of get_block_mask (causal_model.py:109-141)."""
+    _req(q, "q"); _req(k, "k", q.dtype); _req(v, "v", q.dtype)
+    Lq, ldq = _rows2d(q, "q")
+    Lkv, ldk = _rows2d(k, "k")
+    _, ldv = _rows2d(v, "v")
+    hd = q.shape[-1] // heads if q.dim() == 2 else q.shape[-1]
+    if hd != 128:
+        raise _lib.KreaB200Error(f"attention: head_dim {hd} unsupported (128 only)")
+    if out is None:
+        out = torch.empty(Lq, heads * 128, dtype=q.dtype, device=q.device)
+    _, ldo = _rows2d(out, "out")
+    if softmax_scale is None:
+        softmax_scale = 1.0 / math.sqrt(128)
+    lib = _lib.load()
+    rc = lib.kr_attn_fwd(_DT[q.dtype], q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv,
+                         out.data_ptr(), ldo, Lq, Lkv, heads, softmax_scale,
+                         1 if block_len > 0 else 0, block_len, window, _stream())
+    _lib.check(rc, "kr_attn_fwd")
+    _count()
+    return out
+
+
+def ln_modulate(x: torch.Tensor, *, eps: float, weight: Optional[torch.Tensor] = None,
+                bias: Optional[torch.Tensor] = None, mod: Optional[torch.Tensor] = None,
+                shift_idx: int = 0, scale_idx: int = 1, rows_per_frame: int = 0,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LayerNorm over the last dim (+affine) (+ x*(1+mod[f,scale_idx]) + mod[f,shift_idx])."""
+    _req(x, "x", torch.bfloat16)
+    rows, ldx = _rows2d(x, "x")
+    D = x.shape[-1]
+    if out is None:
+        out = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+    _, ldo = _rows2d(out, "out")
+    mod_rows = 0
+    if mod is not None:
+        _req(mod, "mod", torch.bfloat16)
+        if not mod.is_contiguous() or mod.shape[-1] != D:
+            raise _lib.KreaB200Error("ln_modulate: mod must be contiguous [frames, rows, D]")
+        mod_rows = mod.shape[-2]
+    lib = _lib.load()
+    rc = lib.kr_ln_modulate(x.data_ptr(), ldx, out.data_ptr(), ldo, rows, D, eps, _ptr(weight),
+                            _ptr(bias), _ptr(mod), mod_rows, shift_idx, scale_idx, rows_per_frame,
+                            _stream())
+    _lib.check(rc, "kr_ln_modulate")
+    _count()
+    return out
+
+
+def qkv_norm_rope(q, k, v, wq, wk, q_out, k_out, v_out, rope, *, head_dim: int, grid_h: int,
+                  grid_w: int, start_frame: int, eps: float) -> None:
+    """RMSNorm(q), RMSNorm(k), RoPE, write q_out / K-cache slot / V-cache slot (row views)."""
+    _req(q, "q", torch.bfloat16)
+    rows, ldq = _rows2d(q, "q")
+    _, ldk = _rows2d(k, "k")
+    D = q.shape[-1]
+    _, ldqo = _rows2d(q_out, "q_out")
+    _, ldko = _rows2d(k_out, "k_out")
+    ldv = ldvo = 0
+    if v is not None:
+        _, ldv = _rows2d(v, "v")
+        _, ldvo = _rows2d(v_out, "v_out")
+    lib = _lib.load()
+    rc = lib.kr_qkv_norm_rope(q.data_ptr(), ldq, k.data_ptr(), ldk, _ptr(v), ldv, wq.data_ptr(),
+                              wk.data_ptr(), q_out.data_ptr(), ldqo, k_out.data_ptr(), ldko,
+                              _ptr(v_out), ldvo, _ptr(rope), rows, D, head_dim, grid_h, grid_w,
+                              start_frame, eps, _stream())
+    _lib.check(rc, "kr_qkv_norm_rope")
+    _count()
+
+
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, "x", torch.bfloat16)
+    rows, ldx = _rows2d(x, "x")
+    D = x.shape[-1]
+    if out is None:
+        out = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+    _, ldo = _rows2d(out, "out")
+    lib = _lib.load()
+    rc = lib.kr_rmsnorm(x.data_ptr(), ldx, out.data_ptr(), ldo, weight.data_ptr(), rows, D, eps,
+                        _stream())
+    _lib.check(rc, "kr_rmsnorm")
+    _count()
+    return out
+
+
+def add_modulation(modulation: torch.Tensor, e0: torch.Tensor,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """modulation [1, R, D] + e0 [F, R, D] -> [F, R, D] (bf16)."""
+    _req(modulation, "modulation", torch.bfloat16); _req(e0, "e0", torch.bfloat16)
+    F, R, D = e0.shape[-3], e0.shape[-2], e0.shape[-1]
+    if e0.stride(-1) != 1 or e0.stride(-2) != D:
+        raise _lib.KreaB200Error("add_modulation: e0 rows must be contiguous")
+    if out is None:
+        out = torch.empty(F, R, D, dtype=e0.dtype, device=e0.device)
+    lib = _lib.load()
+    rc = lib.kr_add_modulation(modulation.data_ptr(), e0.data_ptr(), e0.stride(-3), out.data_ptr(),
+                               F, R, D, _stream())
+    _lib.check(rc, "kr_add_modulation")
+    _count()
+    return out
+
+
+def activation(x: torch.Tensor, kind: str) -> torch.Tensor:
+    _req(x, "x", torch.bfloat16)
+    if not x.is_contiguous():
+        raise _lib.KreaB200Error("activation: tensor must be contiguous")
+    y = torch.empty_like(x)
+    lib = _lib.load()
+    rc = lib.kr_activation(x.data_ptr(), y.data_ptr(), x.numel(), {"silu": 0, "gelu": 1}[kind],
+                           _stream())
+    _lib.check(rc, "kr_activation")
+    _count()
+    return y
+
+
+def patchify(x: torch.Tensor) -> torch.Tensor:
+    """x [C, F, H, W] (any strides) -> [F*(H/2)*(W/2), 4C] bf16, Conv3d(1,2,2) im2col."""
+    _req(x, "x", torch.bfloat16)
+    C, F, H, W = x.shape
+    out = torch.empty(F * (H // 2) * (W // 2), C * 4, dtype=x.dtype, device=x.device)
+    lib = _lib.load()
+    rc = lib.kr_patchify(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), x.stride(3),
+                         out.data_ptr(), C, F, H, W, _stream())
+    _lib.check(rc, "kr_patchify")
+    _count()
+    return out
+
+
+def unpatchify_x0(head_out: torch.Tensor, xt: Optional[torch.Tensor], sigma: Optional[torch.Tensor],
+                  C: int, F: int, H: int, W: int):
+    """head_out [F*h*w, 4C] -> (flow [F,C,H,W], x0 [F,C,H,W] or None)."""
+    _req(head_out, "head_out", torch.bfloat16)
+    flow = torch.empty(F, C, H, W, dtype=head_out.dtype, device=head_out.device)
+    x0 = None
+    if xt is not None:
+        _req(xt, "xt", torch.bfloat16); _req(sigma, "sigma", torch.float64)
+        if not xt.is_contiguous():
+            raise _lib.KreaB200Error("unpatchify_x0: xt must be contiguous [F,C,H,W]")
+        x0 = torch.empty_like(flow)
+    lib = _lib.load()
+    rc = lib.kr_unpatchify_x0(head_out.data_ptr(), head_out.stride(0), _ptr(xt), _ptr(sigma),
+                              flow.data_ptr(), _ptr(x0), C, F, H, W, _stream())
+    _lib.check(rc, "kr_unpatchify_x0")
+    _count()
+    return flow, x0
