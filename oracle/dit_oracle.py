@@ -170,8 +170,13 @@ class DiTOracle:
             kv_cache["v"][0, :L] = v
             kv_cache["global_end_index"] = L
             kv_cache["local_end_index"] = L
-            mask = block_causal_mask(L, L, mask_args["block_len"], mask_args.get("window", 0), x.device)
-            out = attention(rq, rk, v, mask)
+            # :316-348 — q/k/v are right-padded with ZERO rows to a multiple of 128 and the mask is
+            # built over the padded length, so queries of an incomplete last block also see the
+            # padded keys (score 0, value 0); the padded query rows are sliced away.
+            pad = math.ceil(L / 128) * 128 - L
+            zp = rk.new_zeros(pad, n, d)
+            mask = block_causal_mask(L, L + pad, mask_args["block_len"], mask_args.get("window", 0), x.device)
+            out = attention(rq, torch.cat([rk, zp]), torch.cat([v, zp]), mask)
         else:
             fs = cfg.frame_seqlen_const
             start_frame = current_start // fs                              # :351-352
