@@ -60,10 +60,12 @@ int kr_gemm(int dtype, int epilogue, const void* a, int lda, const void* w, int 
  * mask_mode 0: none (cached self-attention causal_model.py:386-390, cross-attention
  * model.py:214-215); mask_mode 1: block-causal rule of get_block_mask (causal_model.py:109-141)
  * with block_len = frame_seqlen*num_frame_per_block tokens and window = local_attn_size *
- * frame_seqlen tokens (0 = global).  Replaces flash_attn_func / flex_attention. */
+ * frame_seqlen tokens (0 = global); pad_keys = zero-padded key rows (ceil(L/128)*128 - L) that
+ * queries of an incomplete last block also attend on the reference's FlexAttention path
+ * (causal_model.py:316-348).  Replaces flash_attn_func / flex_attention. */
 int kr_attn_fwd(int dtype, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
                 void* out, int ldo, int Lq, int Lkv, int heads, float softmax_scale, int mask_mode,
-                int block_len, int window, void* stream);
+                int block_len, int window, int pad_keys, void* stream);
 
 /* WanLayerNorm (+affine) (+per-frame modulation x*(1+scale)+shift).
  * mod: [frames, mod_rows, D] 16-bit or NULL; w,b: [D] or NULL.

@@ -32,14 +32,14 @@ int kr_gemm(int dtype, int epilogue, const void* a, int lda, const void* w, int 
 
 int kr_attn_fwd(int dtype, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
                 void* out, int ldo, int Lq, int Lkv, int heads, float softmax_scale, int mask_mode,
-                int block_len, int window, void* stream) {
+                int block_len, int window, int pad_keys, void* stream) {
   KR_REQUIRE(q && k && v && out, "null q/k/v/out");
   KR_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (bf16) or 1 (fp16)");
   KR_REQUIRE(mask_mode == 0 || mask_mode == 1, "mask_mode must be 0 or 1");
   kr::AttnParams p;
   p.out = out; p.ldo = ldo; p.Lq = Lq; p.Lkv = Lkv; p.heads = heads;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  p.mask_mode = mask_mode; p.block_len = block_len; p.window = window;
+  p.mask_mode = mask_mode; p.block_len = block_len; p.window = window; p.pad_keys = pad_keys;
   return kr::attn_fwd(dtype, q, ldq, k, ldk, v, ldv, p, static_cast<cudaStream_t>(stream));
 }
 

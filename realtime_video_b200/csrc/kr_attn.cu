@@ -221,11 +221,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t tO = tmem_base + lane_off + 256 + wg * 128;
 
     int row_hi = p.Lkv, row_lo = 0;
+    int n_phantom = 0;
     if (p.mask_mode == 1) {
       const int qq = q_row < p.Lq ? q_row : p.Lq - 1;
       const int hi = (qq / p.block_len + 1) * p.block_len;
       if (p.window > 0) row_lo = hi - p.window > 0 ? hi - p.window : 0;
       if (hi < row_hi) row_hi = hi;
+      if (hi > p.Lkv) n_phantom = hi - p.Lkv < p.pad_keys ? hi - p.Lkv : p.pad_keys;
     }
 
     float m_run = -INFINITY;
@@ -308,7 +310,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // ---- epilogue: O / l -> global ----
     mbar_wait(o_final, 0);
     tc_fence_after();
-    const float inv_l = 1.0f / l_run;
+    float o_scale = 1.0f;
+    if (n_phantom > 0) {
+      // phantom keys: score 0, value 0 -> only the softmax denominator (and max) see them
+      const float m_fin = fmaxf(m_run, 0.f);
+      o_scale = fast_exp2((m_run - m_fin) * sl2);
+      l_run = l_run * o_scale + static_cast<float>(n_phantom) * fast_exp2(-m_fin * sl2);
+    }
+    const float inv_l = o_scale / l_run;
     const bool row_ok = q_row < p.Lq;
     uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + static_cast<size_t>(row_ok ? q_row : 0) * p.ldo +
                      head * kHeadDim;

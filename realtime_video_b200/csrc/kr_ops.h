@@ -40,6 +40,10 @@ struct AttnParams {
   int mask_mode;
   int block_len;       // tokens per causal block (frame_len * frames_per_block)
   int window;          // tokens (local_attn_size * frame_len) or 0
+  // FlexAttention-path quirk (causal_model.py:316-348): q/k/v are zero-padded to a multiple of
+  // 128 rows and queries of an incomplete last block also see those padded keys (score 0,
+  // value 0).  pad_keys = number of such phantom keys after Lkv (0 = off).
+  int pad_keys;
 };
 int attn_fwd(int dtype, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
              const AttnParams& p, cudaStream_t stream);

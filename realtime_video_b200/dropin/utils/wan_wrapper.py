@@ -1,0 +1,234 @@
+"""Drop-in for the reference's ``utils/wan_wrapper.py`` (the L2 boundary).
+
+Same class names, constructor arguments, attributes and call conventions as
+utils/wan_wrapper.py:20-323; the DiT underneath is ``realtime_video_b200.dit.CausalWanModel``
+(hand-written sm_100a kernels behind the C ABI).  ``WanTextEncoder`` (UMT5-XXL, once per prompt,
+off the per-frame path — SURVEY.md §2 row 13) is re-exported from the reference tree when that
+tree is importable further down ``sys.path``.
+"""
+from __future__ import annotations
+
+import importlib.util
+import json
+import os
+import sys
+import types
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from realtime_video_b200 import ops
+from realtime_video_b200.dit import CausalWanModel
+from realtime_video_b200.dropin.utils.scheduler import FlowMatchScheduler, SchedulerInterface
+
+try:  # reference settings.py:1-5
+    from settings import MODEL_FOLDER  # type: ignore
+except Exception:  # noqa: BLE001
+    MODEL_FOLDER = os.environ.get("MODEL_FOLDER", "wan_models")
+
+# Wan 2.1 T2V dimensions (reference wan/configs/wan_t2v_14B.py:21-28, wan_t2v_1_3B.py:21-28)
+KNOWN_CONFIGS = {
+    "14B": dict(dim=5120, ffn_dim=13824, num_heads=40, num_layers=40),
+    "1.3B": dict(dim=1536, ffn_dim=8960, num_heads=12, num_layers=30),
+}
+
+
+def _reference_module(dotted: str, filename: str):
+    """Load ``filename`` of the reference tree from a later sys.path entry (ours shadows it)."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for base in sys.path:
+        cand = os.path.join(base or ".", filename)
+        if os.path.isfile(cand) and not os.path.abspath(cand).startswith(here):
+            spec = importlib.util.spec_from_file_location("_krea_ref_" + dotted.replace(".", "_"), cand)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            return mod
+    return None
+
+
+class _MissingReference(nn.Module):
+    _what = ""
+
+    def __init__(self, *a, **k):
+        super().__init__()
+        raise ImportError(
+            f"{self._what} is not part of the B200 hot path (SURVEY.md §8f); put the reference "
+            f"checkout on sys.path after realtime_video_b200/dropin to use its implementation")
+
+
+def _ref_class(name: str):
+    try:
+        mod = _reference_module("utils.wan_wrapper", os.path.join("utils", "wan_wrapper.py"))
+        if mod is not None:
+            return getattr(mod, name)
+    except Exception:  # noqa: BLE001  (reference import needs its own deps)
+        pass
+    return type(name, (_MissingReference,), {"_what": name})
+
+
+WanTextEncoder = _ref_class("WanTextEncoder")
+
+
+class WanDiffusionWrapper(nn.Module):
+    """utils/wan_wrapper.py:121-323.  Extra keyword arguments (not in the reference) let the
+    model be built without a checkpoint on disk: ``model_config`` (dims), ``device``, ``dtype``."""
+
+    def __init__(self, model_name="Wan2.1-T2V-1.3B", timestep_shift=8.0, is_causal=False,
+                 local_attn_size=-1, sink_size=0, meta_init=False, model_config: Optional[dict] = None,
+                 device=None, dtype=None):
+        super().__init__()
+        if not is_causal:
+            raise NotImplementedError("the bidirectional WanModel is outside the hot path (SURVEY.md §2 row 2)")
+        cfg = dict(model_config) if model_config else self._find_config(model_name)
+        cfg.update(local_attn_size=local_attn_size, sink_size=sink_size)
+        ctx = torch.device("meta") if meta_init else (torch.device(device) if device is not None else None)
+        prev = torch.get_default_dtype()
+        try:
+            if dtype is not None:
+                torch.set_default_dtype(dtype)
+            if ctx is not None:
+                with ctx:
+                    self.model = CausalWanModel(**cfg)
+            else:
+                self.model = CausalWanModel(**cfg)
+        finally:
+            torch.set_default_dtype(prev)
+        self._maybe_load_pretrained(model_name, meta_init)
+        self.model.eval()
+        self.uniform_timestep = not is_causal
+        self.scheduler = FlowMatchScheduler(shift=timestep_shift, sigma_min=0.0, extra_one_step=True)
+        self.scheduler.set_timesteps(1000, training=True)
+        self.seq_len = 32760
+        self._sched_dev = None
+        self.post_init()
+
+    # -- construction helpers ---------------------------------------------------------------
+    @staticmethod
+    def _find_config(model_name: str) -> dict:
+        path = os.path.join(MODEL_FOLDER, model_name, "config.json")
+        keys = ("model_type", "patch_size", "text_len", "in_dim", "dim", "ffn_dim", "freq_dim",
+                "text_dim", "out_dim", "num_heads", "num_layers", "qk_norm", "cross_attn_norm", "eps")
+        if os.path.isfile(path):
+            with open(path) as f:
+                raw = json.load(f)
+            cfg = {k: raw[k] for k in keys if k in raw}
+            if "patch_size" in cfg:
+                cfg["patch_size"] = tuple(cfg["patch_size"])
+            return cfg
+        for tag, dims in KNOWN_CONFIGS.items():
+            if tag in model_name:
+                return dict(dims)
+        raise FileNotFoundError(f"no config.json under {os.path.join(MODEL_FOLDER, model_name)} and "
+                                f"'{model_name}' names no known Wan 2.1 size")
+
+    def _maybe_load_pretrained(self, model_name: str, meta_init: bool) -> None:
+        folder = os.path.join(MODEL_FOLDER, model_name)
+        if meta_init or not os.path.isdir(folder):
+            return
+        files = sorted(f for f in os.listdir(folder)
+                       if f.startswith("diffusion_pytorch_model") and f.endswith(".safetensors"))
+        if not files:
+            return
+        from safetensors.torch import load_file
+        sd = {}
+        for f in files:
+            sd.update(load_file(os.path.join(folder, f)))
+        self.model.load_state_dict(sd, strict=False)
+
+    # -- utils/wan_wrapper.py:181-228 ---------------------------------------------------------
+    def _sigma_table(self, device):
+        key = (device, self.scheduler.sigmas.data_ptr(), self.scheduler.timesteps.data_ptr())
+        if self._sched_dev is None or self._sched_dev[0] != key:
+            self._sched_dev = (key, self.scheduler.sigmas.double().to(device),
+                               self.scheduler.timesteps.double().to(device))
+        return self._sched_dev[1], self._sched_dev[2]
+
+    def _sigma_of(self, timestep: torch.Tensor, device) -> torch.Tensor:
+        sigmas, timesteps = self._sigma_table(device)
+        idx = torch.argmin((timesteps.unsqueeze(0) - timestep.to(device).unsqueeze(1)).abs(), dim=1)
+        return sigmas[idx]
+
+    def _convert_flow_pred_to_x0(self, flow_pred, xt, timestep):
+        """x0 = xt - sigma_t * flow in float64 (:181-205); [B*, C, H, W] inputs."""
+        sigma = self._sigma_of(timestep, flow_pred.device).reshape(-1, 1, 1, 1)
+        return (xt.double() - sigma * flow_pred.double()).to(flow_pred.dtype)
+
+    @staticmethod
+    def _convert_x0_to_flow_pred(scheduler, x0_pred, xt, timestep):
+        """(:207-228)"""
+        dt = x0_pred.dtype
+        sig, ts = scheduler.sigmas.double().to(x0_pred.device), scheduler.timesteps.double().to(x0_pred.device)
+        idx = torch.argmin((ts.unsqueeze(0) - timestep.unsqueeze(1)).abs(), dim=1)
+        return ((xt.double() - x0_pred.double()) / sig[idx].reshape(-1, 1, 1, 1)).to(dt)
+
+    # -- utils/wan_wrapper.py:230-301 ---------------------------------------------------------
+    def forward(self, noisy_image_or_video: torch.Tensor, conditional_dict: dict,
+                timestep: torch.Tensor, kv_cache: Optional[List[dict]] = None,
+                crossattn_cache: Optional[List[dict]] = None, current_start: Optional[int] = None,
+                classify_mode: Optional[bool] = False, concat_time_embeddings: Optional[bool] = False,
+                clean_x: Optional[torch.Tensor] = None, aug_t: Optional[torch.Tensor] = None,
+                cache_start: Optional[int] = None):
+        """noisy [B, F, 16, h, w], timestep [B, F] -> (flow_pred, pred_x0) of the same shape/dtype;
+        mutates the cache dicts in place like the reference."""
+        if kv_cache is None or clean_x is not None or classify_mode:
+            raise NotImplementedError("only the KV-cached causal forward is on the hot path")
+        prompt_embeds = conditional_dict["prompt_embeds"]
+        B, Fr, C, H, W = noisy_image_or_video.shape
+        model = self.model
+        flows, x0s = [], []
+        for b in range(B):
+            kv_b = kv_cache if B == 1 else [
+                {"k": c["k"][b:b + 1], "v": c["v"][b:b + 1], "global_end_index": c["global_end_index"],
+                 "local_end_index": c["local_end_index"]} for c in kv_cache]
+            ca_b = crossattn_cache if B == 1 else None   # per-sample prompts: no shared cache
+            head_out, _ = model.forward_tokens(noisy_image_or_video[b].permute(1, 0, 2, 3),
+                                               timestep[b], prompt_embeds[b], kv_b, ca_b,
+                                               int(current_start or 0))
+            xt = noisy_image_or_video[b].to(head_out.dtype).contiguous()
+            sigma = self._sigma_of(timestep[b].flatten(), head_out.device)
+            flow, x0 = ops.unpatchify_x0(head_out, xt, sigma, model.out_dim, Fr, H, W)
+            flows.append(flow)
+            x0s.append(x0)
+            if B > 1 and b == B - 1:
+                for c, cb in zip(kv_cache, kv_b):
+                    c["global_end_index"], c["local_end_index"] = cb["global_end_index"], cb["local_end_index"]
+        return torch.stack(flows), torch.stack(x0s)
+
+    def get_scheduler(self) -> SchedulerInterface:
+        """(:303-315) binds the interface's conversion helpers onto the scheduler instance."""
+        s = self.scheduler
+        for name in ("convert_x0_to_noise", "convert_noise_to_x0", "convert_velocity_to_x0"):
+            setattr(s, name, types.MethodType(getattr(SchedulerInterface, name), s))
+        return s
+
+    def post_init(self):
+        self.get_scheduler()
+
+    def enable_gradient_checkpointing(self) -> None:
+        raise NotImplementedError("inference-only implementation")
+
+
+class WanVAEWrapper(nn.Module):
+    """utils/wan_wrapper.py:58-118 — classic-path VAE (decode_to_pixel / encode_to_latent)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        from realtime_video_b200.vae import WanVAEDecoderCore   # lazy: VAE kernels
+        self.mean = torch.tensor(WanVAEDecoderCore.MEAN, dtype=torch.float32)
+        self.std = torch.tensor(WanVAEDecoderCore.STD, dtype=torch.float32)
+        self.core = WanVAEDecoderCore(*args, **kwargs)
+
+    def decode_to_pixel(self, latent: torch.Tensor, use_cache: bool = False) -> torch.Tensor:
+        """latent [B, F, 16, h, w] -> pixels [B, F', 3, H, W] fp32 in [-1, 1]."""
+        outs = []
+        for b in range(latent.shape[0]):
+            cache = self.core.persistent_cache if use_cache else [None] * self.core.num_cache_slots
+            px, cache = self.core.decode(latent[b:b + 1], cache)
+            if use_cache:
+                self.core.persistent_cache = cache
+            outs.append(px[0])
+        return torch.stack(outs)
+
+    def encode_to_latent(self, pixel: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError("VAE encoder is a 'next' row (SURVEY.md §8f.1)")

@@ -94,7 +94,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, heads: int,
               out: Optional[torch.Tensor] = None, softmax_scale: Optional[float] = None,
-              block_len: int = 0, window: int = 0) -> torch.Tensor:
+              block_len: int = 0, window: int = 0, pad_keys: int = 0) -> torch.Tensor:
     """q [Lq, heads*128], k/v [Lkv, heads*128] (row pitch free) -> [Lq, heads*128].
 
     block_len > 0 selects the block-causal mask of get_block_mask (causal_model.py:109-141)."""
@@ -113,7 +113,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, heads: int,
     lib = _lib.load()
     rc = lib.kr_attn_fwd(_DT[q.dtype], q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv,
                          out.data_ptr(), ldo, Lq, Lkv, heads, softmax_scale,
-                         1 if block_len > 0 else 0, block_len, window, _stream())
+                         1 if block_len > 0 else 0, block_len, window, pad_keys, _stream())
     _lib.check(rc, "kr_attn_fwd")
     _count()
     return out
