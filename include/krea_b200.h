@@ -50,7 +50,7 @@ const char* kr_last_error(void);
  *   ffn.0 + GELU(tanh), ffn.2   wan/modules/causal_model.py:433-435
  *   cross-attn q/k/v/o          wan/modules/model.py:183-190, :226-227
  *   patch/text/time embeddings, time_projection, head   causal_model.py:874-902, :507-522
- * Needs K % 64 == 0, N % 32 == 0, ld* % 8 == 0.  bias/residual/gate may be NULL when unused. */
+ * Needs K % 8 == 0, N % 32 == 0, ld* % 8 == 0.  bias/residual/gate may be NULL when unused. */
 int kr_gemm(int dtype, int epilogue, const void* a, int lda, const void* w, int ldw,
             const void* bias, void* out, int ldc, int M, int N, int K, const void* residual,
             int ldr, const void* gate, int gate_stride, int rows_per_gate, float alpha,
@@ -102,6 +102,41 @@ int kr_patchify(const void* x, long sc, long sf, long sh, long sw, void* out, in
  * (utils/wan_wrapper.py:181-205): flow,x0,xt are [F,C,H,W]; sigma: double[F]; x0 may be NULL */
 int kr_unpatchify_x0(const void* head_out, int ldh, const void* xt, const double* sigma,
                      void* flow, void* x0, int C, int F, int H, int W, void* stream);
+
+/* ---- causal 3D VAE decoder (channels-last activations [frames, H, W, C], fp16 or bf16) ---- */
+
+/* CausalConv3d / Conv2d / 1x1x1 conv as a tcgen05 implicit GEMM (wan/modules/vae.py:17-36,
+ * :175-209; demo_utils/vae_block3.py:46-91, :386-443).  `in` holds t_in >= T + kt - 1 frames:
+ * the (kt-1) cached frames in front of the T new ones (read in place, no cat/pad); spatial zero
+ * padding is the TMA out-of-bounds fill.  weight: [w_rows, kt*kh*kw*cin] (tap-major, cin
+ * contiguous).  (cin, n) must be one of the decoder's channel pairs: (64,384) (384,384)
+ * (192,384) (384,192) (192,192) (192,96) (96,96) (96,16); n is the padded Cout, cout the real
+ * one.  tile_w*tile_h == 128.  Outputs (any subset), element strides per pixel / per frame:
+ *   out_raw  = cast(acc + bias [+ residual])
+ *   out_norm = SiLU(RMS_norm_C(out_raw) * sqrt(cout) * gamma)     (vae.py:39-54, :184-186)
+ *   out_pix  = clamp(out_raw, -1, 1) as fp32 [T, cout, H, W]       (vae_block3.py:226) */
+int kr_vae_conv3d(int dtype, int cin, int n, const void* in, int t_in, const void* weight,
+                  int w_rows, const void* bias, int cout, int T, int H, int W, int tile_w, int tile_h,
+                  int kt, int kh, int kw, void* out_raw, long raw_pix, long raw_frame, void* out_norm,
+                  long norm_pix, long norm_frame, const void* gamma, const void* residual,
+                  long res_pix, long res_frame, float* out_pix, void* stream);
+
+/* y = RMS_norm_C(x) * sqrt(C) * gamma [-> SiLU], x,y [pixels, C]  (vae.py:39-54) */
+int kr_vae_rmsnorm_silu(int dtype, const void* x, void* y, const void* gamma, long pixels, int C,
+                        int do_silu, void* stream);
+
+/* nearest-neighbour 2x spatial upsample [T,H,W,C] -> [T,2H,2W,C]  (vae.py:57-63) */
+int kr_vae_upsample2x(const void* in, void* out, int T, int H, int W, int C, void* stream);
+
+/* z [T,16,H,W] (element strides zt,zc,zh,zw): x = z/inv_std + mean, y = conv2_1x1x1(x), written
+ * channels-last and zero-padded to 64 channels  (demo_utils/vae_block3.py:205-214) */
+int kr_vae_scale_input(int dtype, const void* z, long zt, long zc, long zh, long zw,
+                       const void* mean, const void* inv_std, const void* w2, const void* b2,
+                       void* out, int T, int H, int W, void* stream);
+
+/* p[r, :cols] = softmax(s[r, :cols]) ; fp32 in, 16-bit out  (vae.py:239-244 attention block) */
+int kr_softmax_rows(int dtype, const float* s, long ld, void* p, long ldo, int rows, int cols,
+                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,197 @@
+"""TEST INFRASTRUCTURE — CPU oracle for the causal 3D VAE decoder (not shipped, not measured).
+
+Plain-torch restatement (NCHW, F.conv3d) of ``VAEDecoderWrapper.forward`` —
+demo_utils/vae_block3.py:195-230 (wrapper), :386-443 (VAEDecoder3d.forward), :46-91 (Resample),
+wan/modules/vae.py:17-36 (CausalConv3d), :39-54 (RMS_norm), :191-209 (ResidualBlock),
+:229-251 (AttentionBlock).  Parameters come as a dict keyed like the reference state dict
+(``decoder.conv1.weight`` ...).  The feature cache is a dict {slot: tensor [1,C,<=2,H,W]}.
+Pinned by tests/golden/make_vae_goldens.py (reference run on CPU) via tests/test_oracle_vae.py.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference import this.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+MEAN = [-0.7571, -0.7089, -0.9113, 0.1075, -0.1745, 0.9653, -0.1517, 1.5508,
+        0.4134, -0.0715, 0.5517, -0.3632, -0.1922, -0.9497, 0.2503, -0.2921]
+STD = [2.8184, 1.4541, 2.3275, 2.6558, 1.2196, 1.7708, 2.6052, 2.0743,
+       3.2687, 2.1526, 2.8652, 1.5579, 1.6382, 1.1253, 2.8251, 1.9160]
+
+
+def causal_conv3d(x, w, b, cache=None):
+    """vae.py:27-36: cat cache on T, zero-pad W/H by k//2 and T-front by (k_t - 1) - cache_T."""
+    kt, kh, kw = w.shape[2:]
+    pad_t = kt - 1
+    if cache is not None and pad_t > 0:
+        x = torch.cat([cache, x], dim=2)
+        pad_t -= cache.shape[2]
+    x = F.pad(x, (kw // 2, kw // 2, kh // 2, kh // 2, pad_t, 0))
+    return F.conv3d(x, w, b)
+
+
+def rms_norm(x, gamma):
+    """vae.py:51-54 with channel_first: normalize over dim 1, * sqrt(C) * gamma."""
+    return F.normalize(x, dim=1) * (x.shape[1] ** 0.5) * gamma
+
+
+class VAEDecoderOracle:
+    def __init__(self, params):
+        self.p = params
+        self.n_up = 15                          # decoder.upsamples.0 .. 14
+        self.kinds = {3: "up3d", 7: "up3d", 11: "up2d"}
+
+    def _cached_conv(self, name, x, cache, idx):
+        """ResidualBlock / conv1 / head cache rule (vae.py:196-206): keep the last 2 input frames,
+        borrowing the previous last frame when the chunk has a single frame."""
+        i = idx[0]
+        cx = x[:, :, -2:].clone()
+        if cx.shape[2] < 2 and cache.get(i) is not None:
+            cx = torch.cat([cache[i][:, :, -1:], cx], dim=2)
+        y = causal_conv3d(x, self.p[name + ".weight"], self.p[name + ".bias"], cache.get(i))
+        cache[i] = cx
+        idx[0] += 1
+        return y
+
+    def _res(self, pre, x, cache, idx):
+        p = self.p
+        h = x
+        if (pre + ".shortcut.weight") in p:
+            h = causal_conv3d(x, p[pre + ".shortcut.weight"], p[pre + ".shortcut.bias"])
+        y = F.silu(rms_norm(x, p[pre + ".residual.0.gamma"]))
+        y = self._cached_conv(pre + ".residual.2", y, cache, idx)
+        y = F.silu(rms_norm(y, p[pre + ".residual.3.gamma"]))
+        y = self._cached_conv(pre + ".residual.6", y, cache, idx)
+        return y + h
+
+    def _attn(self, pre, x):
+        p = self.p
+        b, c, t, h, w = x.shape
+        y = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w)
+        y = rms_norm(y, p[pre + ".norm.gamma"])
+        qkv = F.conv2d(y, p[pre + ".to_qkv.weight"], p[pre + ".to_qkv.bias"])
+        q, k, v = qkv.reshape(b * t, 1, 3 * c, h * w).permute(0, 1, 3, 2).chunk(3, dim=-1)
+        o = F.scaled_dot_product_attention(q, k, v)
+        o = o.squeeze(1).permute(0, 2, 1).reshape(b * t, c, h, w)
+        o = F.conv2d(o, p[pre + ".proj.weight"], p[pre + ".proj.bias"])
+        return o.reshape(b, t, c, h, w).permute(0, 2, 1, 3, 4) + x
+
+    def _resample(self, pre, mode, x, cache, idx):
+        p = self.p
+        b, c, t, h, w = x.shape
+        if mode == "up3d":                                   # vae_block3.py:48-66
+            i = idx[0]
+            if cache.get(i) is None:
+                cache[i] = torch.zeros(b, c, 2, h, w, dtype=x.dtype, device=x.device)
+                idx[0] += 1
+            else:
+                cx = x[:, :, -2:].clone()
+                if cx.shape[2] < 2:
+                    pad = torch.where(cache[i][:, :, -1:] == 0, torch.zeros_like(cx), cx)
+                    cx = torch.cat([pad, cx], dim=2)
+                y = causal_conv3d(x, p[pre + ".time_conv.weight"], p[pre + ".time_conv.bias"], cache[i])
+                cache[i] = cx
+                idx[0] += 1
+                y = y.reshape(b, 2, c, t, h, w)
+                x = torch.stack((y[:, 0], y[:, 1]), 3).reshape(b, c, t * 2, h, w)
+        t = x.shape[2]
+        y = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w)
+        y = F.interpolate(y.float(), scale_factor=(2.0, 2.0), mode="nearest").type_as(y)   # vae.py:57-63
+        y = F.conv2d(y, p[pre + ".resample.1.weight"], p[pre + ".resample.1.bias"], padding=1)
+        return y.reshape(b, t, c // 2, 2 * h, 2 * w).permute(0, 2, 1, 3, 4)
+
+    def decode_frame(self, x, cache):
+        """VAEDecoder3d.forward (vae_block3.py:386-443) on one latent frame [1, 16, 1, h, w]."""
+        idx = [0]
+        x = self._cached_conv("decoder.conv1", x, cache, idx)
+        x = self._res("decoder.middle.0", x, cache, idx)
+        x = self._attn("decoder.middle.1", x)
+        x = self._res("decoder.middle.2", x, cache, idx)
+        for i in range(self.n_up):
+            pre = f"decoder.upsamples.{i}"
+            if i in self.kinds:
+                x = self._resample(pre, self.kinds[i], x, cache, idx)
+            else:
+                x = self._res(pre, x, cache, idx)
+        x = F.silu(rms_norm(x, self.p["decoder.head.0.gamma"]))
+        # head conv: same cache rule (the reference zero-fills a 2-frame buffer first, which is
+        # the zero padding again, vae_block3.py:428-437)
+        return self._cached_conv("decoder.head.2", x, cache, idx)
+
+    def forward(self, z, cache):
+        """z [1, T, 16, h, w] -> (pixels [1, T', 3, H, W] fp32 clamped to [-1, 1], cache)."""
+        p = self.p
+        z = z.permute(0, 2, 1, 3, 4)
+        dt = z.dtype
+        mean = torch.tensor(MEAN, dtype=torch.float32).to(dt).view(1, 16, 1, 1, 1)
+        inv_std = (1.0 / torch.tensor(STD, dtype=torch.float32).to(dt)).view(1, 16, 1, 1, 1)
+        z = z / inv_std + mean                                       # vae_block3.py:205-209
+        x = causal_conv3d(z, p["conv2.weight"], p["conv2.bias"])
+        outs = [self.decode_frame(x[:, :, i:i + 1], cache) for i in range(x.shape[2])]
+        out = torch.cat(outs, dim=2).float().clamp_(-1, 1)
+        return out.permute(0, 2, 1, 3, 4), cache
+
+
+def synthetic_vae_params(seed: int = 0, dim: int = 96, z_dim: int = 16):
+    """Deterministic decoder weights independent of module construction order: every tensor is
+    drawn from its own generator seeded by (seed, key).  Conv weights ~ N(0, 1/fan_in) * 1.4,
+    biases ~ N(0, .02), gammas ~ 1 + N(0, .1)."""
+    import zlib
+    shapes = {}
+    dims = [dim * 4, dim * 4, dim * 4, dim * 2, dim]
+
+    def conv3(name, ci, co, k):
+        shapes[name + ".weight"] = (co, ci, *k)
+        shapes[name + ".bias"] = (co,)
+
+    def res(pre, ci, co):
+        shapes[pre + ".residual.0.gamma"] = (ci, 1, 1, 1)
+        conv3(pre + ".residual.2", ci, co, (3, 3, 3))
+        shapes[pre + ".residual.3.gamma"] = (co, 1, 1, 1)
+        conv3(pre + ".residual.6", co, co, (3, 3, 3))
+        if ci != co:
+            conv3(pre + ".shortcut", ci, co, (1, 1, 1))
+
+    conv3("conv2", z_dim, z_dim, (1, 1, 1))
+    conv3("decoder.conv1", z_dim, dims[0], (3, 3, 3))
+    res("decoder.middle.0", dims[0], dims[0])
+    shapes["decoder.middle.1.norm.gamma"] = (dims[0], 1, 1)
+    shapes["decoder.middle.1.to_qkv.weight"] = (3 * dims[0], dims[0], 1, 1)
+    shapes["decoder.middle.1.to_qkv.bias"] = (3 * dims[0],)
+    shapes["decoder.middle.1.proj.weight"] = (dims[0], dims[0], 1, 1)
+    shapes["decoder.middle.1.proj.bias"] = (dims[0],)
+    res("decoder.middle.2", dims[0], dims[0])
+    n = 0
+    cin = dims[0]
+    plan = [(dims[0], dims[1], "up3d"), (dims[1] // 2, dims[2], "up3d"), (dims[2] // 2, dims[3], "up2d"),
+            (dims[3] // 2, dims[4], None)]
+    for ci, co, up in plan:
+        cin = ci
+        for _ in range(3):
+            res(f"decoder.upsamples.{n}", cin, co)
+            cin = co
+            n += 1
+        if up is not None:
+            pre = f"decoder.upsamples.{n}"
+            shapes[pre + ".resample.1.weight"] = (co // 2, co, 3, 3)
+            shapes[pre + ".resample.1.bias"] = (co // 2,)
+            if up == "up3d":
+                conv3(pre + ".time_conv", co, 2 * co, (3, 1, 1))
+            n += 1
+    shapes["decoder.head.0.gamma"] = (dims[4], 1, 1, 1)
+    conv3("decoder.head.2", dims[4], 3, (3, 3, 3))
+    out = {}
+    for k, shp in shapes.items():
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(k.encode())) % (2 ** 31))
+        t = torch.randn(shp, generator=g)
+        if k.endswith("gamma"):
+            t = 1.0 + 0.1 * t
+        elif k.endswith("bias"):
+            t = 0.02 * t
+        else:
+            fan_in = 1
+            for d in shp[1:]:
+                fan_in *= d
+            t = t * (1.4 / fan_in ** 0.5)
+        out[k] = t
+    return out

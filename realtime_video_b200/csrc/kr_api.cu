@@ -3,6 +3,8 @@
 #include "kr_common.cuh"
 #include "kr_ops.h"
 
+#include <cmath>
+
 
 #define KR_REQUIRE(cond, msg)                 \
   do {                                        \
@@ -102,6 +104,50 @@ int kr_unpatchify_x0(const void* head_out, int ldh, const void* xt, const double
   KR_REQUIRE(x0 == nullptr || (xt && sigma), "x0 requested without xt/sigma");
   return kr::unpatchify_x0(head_out, ldh, xt, sigma, flow, x0, C, F, H, W,
                            static_cast<cudaStream_t>(stream));
+}
+
+int kr_vae_conv3d(int dtype, int cin, int n, const void* in, int t_in, const void* weight,
+                  int w_rows, const void* bias, int cout, int T, int H, int W, int tile_w, int tile_h,
+                  int kt, int kh, int kw, void* out_raw, long raw_pix, long raw_frame, void* out_norm,
+                  long norm_pix, long norm_frame, const void* gamma, const void* residual,
+                  long res_pix, long res_frame, float* out_pix, void* stream) {
+  KR_REQUIRE(in && weight, "null input/weight");
+  KR_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (bf16) or 1 (fp16)");
+  KR_REQUIRE(out_raw || out_norm || out_pix, "no output requested");
+  kr::ConvParams p;
+  p.T = T; p.H = H; p.W = W; p.TW = tile_w; p.TH = tile_h; p.KT = kt; p.KH = kh; p.KW = kw;
+  p.cout = cout;
+  p.out_raw = out_raw; p.raw_pix = raw_pix; p.raw_frame = raw_frame;
+  p.out_norm = out_norm; p.norm_pix = norm_pix; p.norm_frame = norm_frame;
+  p.out_pix = out_pix; p.bias = bias;
+  p.residual = residual; p.res_pix = res_pix; p.res_frame = res_frame;
+  p.gamma = gamma; p.norm_scale = sqrtf(static_cast<float>(cout));
+  return kr::vae_conv(dtype, cin, n, in, t_in, weight, w_rows, p, static_cast<cudaStream_t>(stream));
+}
+
+int kr_vae_rmsnorm_silu(int dtype, const void* x, void* y, const void* gamma, long pixels, int C,
+                        int do_silu, void* stream) {
+  KR_REQUIRE(x && y && gamma, "null pointer");
+  return kr::vae_rmsnorm_silu(dtype, x, y, gamma, pixels, C, do_silu, static_cast<cudaStream_t>(stream));
+}
+
+int kr_vae_upsample2x(const void* in, void* out, int T, int H, int W, int C, void* stream) {
+  KR_REQUIRE(in && out, "null pointer");
+  return kr::vae_upsample2x(in, out, T, H, W, C, static_cast<cudaStream_t>(stream));
+}
+
+int kr_vae_scale_input(int dtype, const void* z, long zt, long zc, long zh, long zw,
+                       const void* mean, const void* inv_std, const void* w2, const void* b2,
+                       void* out, int T, int H, int W, void* stream) {
+  KR_REQUIRE(z && mean && inv_std && w2 && b2 && out, "null pointer");
+  return kr::vae_scale_input(dtype, z, zt, zc, zh, zw, mean, inv_std, w2, b2, out, T, H, W,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int kr_softmax_rows(int dtype, const float* s, long ld, void* p, long ldo, int rows, int cols,
+                    void* stream) {
+  KR_REQUIRE(s && p, "null pointer");
+  return kr::softmax_rows(dtype, s, ld, p, ldo, rows, cols, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

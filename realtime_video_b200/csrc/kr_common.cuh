@@ -163,13 +163,15 @@ KR_DEVICE void tc_fence_after() {
 // MN-major SW128 operand ([k][mn] with mn contiguous, 64 mn-elements = 128 B per
 //   k-row): 8 k-rows 128 B apart form a 1024 B atom; the next 8 k-rows are SBO
 //   bytes further, the next 64 mn-elements LBO bytes further.
-KR_DEVICE uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type: 2 = SWIZZLE_128B (default), 4 = SWIZZLE_64B, 6 = SWIZZLE_32B, 0 = none
+KR_DEVICE uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                  uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;   // version
-  d |= static_cast<uint64_t>(2) << 61;   // SWIZZLE_128B
+  d |= static_cast<uint64_t>(layout_type) << 61;
   return d;
 }
 
@@ -302,7 +304,7 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 // generic N-d (<=5) map of 16-bit elements; dims/strides innermost first; strides in bytes
 // for dims 1..n-1.
 int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                 const uint64_t* strides_bytes, const uint32_t* box, bool is_bf16, bool swizzle128);
+                 const uint64_t* strides_bytes, const uint32_t* box, bool is_bf16, int swizzle_bytes);
 
 int sm_count();
 

@@ -63,7 +63,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int num_n = p.N / BLOCK_N;
   const int num_tiles = num_m * num_n;
-  const int num_k = p.K / BLOCK_K;
+  const int num_k = (p.K + BLOCK_K - 1) / BLOCK_K;   // K tail: TMA zero-fills both operands
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -342,8 +342,8 @@ int gemm_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, 
     set_last_error("gemm: non-positive shape M=%d N=%d K=%d", p.M, p.N, p.K);
     return KR_ERR_INVALID_ARG;
   }
-  if (p.K % BLOCK_K != 0 || p.N % 32 != 0 || lda % 8 != 0 || ldw % 8 != 0 || p.ldc % 8 != 0) {
-    set_last_error("gemm: unsupported shape M=%d N=%d K=%d (need K%%64==0, N%%32==0, ld%%8==0)",
+  if (p.K % 8 != 0 || p.N % 32 != 0 || lda % 8 != 0 || ldw % 8 != 0 || p.ldc % 8 != 0) {
+    set_last_error("gemm: unsupported shape M=%d N=%d K=%d (need K%%8==0, N%%32==0, ld%%8==0)",
                    p.M, p.N, p.K);
     return KR_ERR_UNSUPPORTED_SHAPE;
   }

@@ -52,7 +52,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                 const uint64_t* strides_bytes, const uint32_t* box, bool is_bf16, bool swizzle128) {
+                 const uint64_t* strides_bytes, const uint32_t* box, bool is_bf16, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -75,7 +75,9 @@ int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* d
   CUresult r = fn(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                   static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstride, bdim,
                   estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,...] "
@@ -92,7 +94,7 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
   uint64_t dims[2] = {cols, rows};
   uint64_t strides[1] = {row_pitch_elems * 2};
   uint32_t box[2] = {box_cols, box_rows};
-  return make_tmap_nd(out, base, 2, dims, strides, box, is_bf16, true);
+  return make_tmap_nd(out, base, 2, dims, strides, box, is_bf16, 128);
 }
 
 }  // namespace kr

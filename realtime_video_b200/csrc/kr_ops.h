@@ -74,4 +74,27 @@ int patchify(const void* x, long sc, long sf, long sh, long sw, void* out, int C
              int W, cudaStream_t stream);
 int unpatchify_x0(const void* head_out, int ldh, const void* xt, const double* sigma, void* flow,
                   void* x0, int C, int F, int H, int W, cudaStream_t stream);
+struct ConvParams {
+  int T, H, W;          // output frames / height / width
+  int TW, TH;           // spatial tile, TW * TH == 128
+  int KT, KH, KW;       // taps
+  int cout;             // real output channels (<= N)
+  void* out_raw; long raw_pix, raw_frame;       // 16-bit; element strides per pixel / frame
+  void* out_norm; long norm_pix, norm_frame;    // 16-bit, RMS_norm*gamma -> SiLU
+  float* out_pix;                               // fp32 [T, cout, H, W], clamp(-1, 1)
+  const void* bias;                             // [cout] 16-bit or null
+  const void* residual; long res_pix, res_frame;
+  const void* gamma;                            // [cout] for out_norm
+  float norm_scale;                             // sqrt(C)
+};
+int vae_conv(int dtype, int cin, int n, const void* in, int t_in, const void* wgt, int w_rows,
+             const ConvParams& p, cudaStream_t stream);
+int vae_rmsnorm_silu(int dtype, const void* x, void* y, const void* gamma, long pixels, int C,
+                     int do_silu, cudaStream_t stream);
+int vae_upsample2x(const void* in, void* out, int T, int H, int W, int C, cudaStream_t stream);
+int vae_scale_input(int dtype, const void* z, long zt, long zc, long zh, long zw, const void* mean,
+                    const void* inv_std, const void* w2, const void* b2, void* out, int T, int H,
+                    int W, cudaStream_t stream);
+int softmax_rows(int dtype, const float* s, long ld, void* pout, long ldo, int rows, int cols,
+                 cudaStream_t stream);
 }  // namespace kr

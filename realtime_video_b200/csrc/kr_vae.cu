@@ -1,0 +1,703 @@
+// kr_vae.cu — causal 3D VAE decoder kernels for sm_100a (channels-last activations).
+//
+// conv3d_igemm : CausalConv3d / Conv2d / 1x1x1 conv as an implicit GEMM on tcgen05 + TMEM.
+//   Reference: wan/modules/vae.py:17-36 (CausalConv3d: cat(cache, x) on T, zero-pad H/W, cuDNN
+//   conv), :175-209 (ResidualBlock: RMS_norm -> SiLU -> conv, twice, + shortcut),
+//   demo_utils/vae_block3.py:46-91 (Resample), :386-443 (VAEDecoder3d).
+//   Layout: activations are [frames, H, W, C] (C contiguous).  The input buffer of a causal
+//   conv holds the 2 cached frames in front of the T new ones, so tap kt of output frame t reads
+//   buffer frame t + kt IN PLACE (no torch.cat / F.pad copies); spatial zero padding is the TMA
+//   out-of-bounds fill.  GEMM view per output tile: M = 128 pixels (a TH x TW patch of one
+//   frame), N = Cout, K = taps * Cin; the A tile of tap (kt,kh,kw) is ONE 4-D TMA box
+//   {64 ch, TW, TH, 1} at (c0, w0+kw-1, h0+kh-1, t+kt) landing in the canonical K-major
+//   SWIZZLE_128B layout; weights are pre-permuted to [Cout, taps*Cin].
+//   Epilogue (thread = pixel, all Cout columns of its TMEM lane): bias, optional residual add,
+//   optional raw store, optional fused RMS_norm(channel) * sqrt(C) * gamma -> SiLU store
+//   (vae.py:39-54, :184-186) for the NEXT conv's input, or clamp -> fp32 NCHW pixels.
+// Small HBM-bound kernels: latent un-scaling + conv2 (vae_block3.py:205-214), RMS_norm+SiLU,
+//   nearest 2x upsample (vae.py:57-63), row softmax for the middle attention block.
+#include "kr_common.cuh"
+#include "kr_ops.h"
+
+namespace kr {
+
+static constexpr int kConvThreads = 192;
+
+template <int CIN, int N>
+struct ConvCfg {
+  static constexpr bool kHas32 = (CIN % 64) == 32;
+  static constexpr int kChunks = CIN / 64;                       // full 64-channel chunks per tap
+  static constexpr int kStagesPerTap = kHas32 ? 1 : kChunks;    // CIN=96: one stage = 64 + 32 ch
+  static constexpr int kA64 = 128 * 128;                          // bytes
+  static constexpr int kA32 = kHas32 ? 128 * 64 : 0;
+  static constexpr int kB64 = N * 128;
+  static constexpr int kB32 = kHas32 ? N * 64 : 0;
+  static constexpr int kStageBytes = kA64 + kA32 + kB64 + kB32;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kMmaN = N > 256 ? N / 2 : N;
+  static constexpr int kMmaSplit = N / kMmaN;
+  static constexpr int kNumAcc = N > 256 ? 1 : 2;
+  static constexpr int kAccStride = N;                            // TMEM columns between buffers
+  static constexpr int kTmemCols = (kNumAcc * N) <= 32 ? 32 : (kNumAcc * N) <= 64 ? 64
+                                   : (kNumAcc * N) <= 128 ? 128 : (kNumAcc * N) <= 256 ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static_assert(kStages >= 2, "pipeline needs >= 2 stages");
+  static_assert(kB64 % 1024 == 0 && (kB32 % 512) == 0, "swizzle alignment of B tiles");
+};
+
+
+KR_DEVICE void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+template <bool kBf16>
+KR_DEVICE float rnd16(float x) {
+  return kBf16 ? __bfloat162float(__float2bfloat16_rn(x)) : __half2float(__float2half_rn(x));
+}
+template <bool kBf16>
+KR_DEVICE float2 unpack16(uint32_t u) {
+  return kBf16 ? unpack_bf16x2(u) : unpack_f16x2(u);
+}
+template <bool kBf16>
+KR_DEVICE uint32_t pack16(float a, float b) {
+  return kBf16 ? pack_bf16x2(a, b) : pack_f16x2(a, b);
+}
+template <bool kBf16>
+KR_DEVICE float load16(const uint16_t* p) {
+  uint16_t u = *p;
+  return kBf16 ? __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&u))
+               : __half2float(*reinterpret_cast<__half*>(&u));
+}
+
+template <int CIN, int N, bool kBf16>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in64, const __grid_constant__ CUtensorMap tm_in32,
+                  const __grid_constant__ CUtensorMap tm_w64, const __grid_constant__ CUtensorMap tm_w32,
+                  const ConvParams p) {
+  using Cfg = ConvCfg<CIN, N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  // per-stage layout: [A64 | B64 | A32 | B32]; all offsets multiples of 1024 (A32/B32: 512)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_w = (p.W + p.TW - 1) / p.TW;
+  const int tiles_h = (p.H + p.TH - 1) / p.TH;
+  const int tiles_per_frame = tiles_w * tiles_h;
+  const int num_tiles = p.T * tiles_per_frame;
+  const int taps = p.KT * p.KH * p.KW;
+  const int pad_h = p.KH / 2, pad_w = p.KW / 2;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_in64);
+    prefetch_tmap(&tm_w64);
+    if (Cfg::kHas32) {
+      prefetch_tmap(&tm_in32);
+      prefetch_tmap(&tm_w32);
+    }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < Cfg::kStages; ++i) {
+        mbar_init(&full_bar[i], 1);
+        mbar_init(&empty_bar[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tmem_full[i], 1);
+        mbar_init(&tmem_empty[i], 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::kTmemCols>(tmem_base_smem);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int t = tile / tiles_per_frame;
+        const int rem = tile % tiles_per_frame;
+        const int h0 = (rem / tiles_w) * p.TH;
+        const int w0 = (rem % tiles_w) * p.TW;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int kt = tap / (p.KH * p.KW);
+          const int kh = (tap / p.KW) % p.KH;
+          const int kw = tap % p.KW;
+          for (int c = 0; c < Cfg::kStagesPerTap; ++c) {
+            uint8_t* st = smem + stage * Cfg::kStageBytes;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_4d(st, &tm_in64, &full_bar[stage], c * 64, w0 + kw - pad_w, h0 + kh - pad_h,
+                        t + kt);
+#pragma unroll
+            for (int j = 0; j < Cfg::kMmaSplit; ++j)
+              tma_load_2d(st + Cfg::kA64 + j * Cfg::kMmaN * 128, &tm_w64, &full_bar[stage],
+                          tap * CIN + c * 64, j * Cfg::kMmaN);
+            if (Cfg::kHas32) {
+              tma_load_4d(st + Cfg::kA64 + Cfg::kB64, &tm_in32, &full_bar[stage], 64,
+                          w0 + kw - pad_w, h0 + kh - pad_h, t + kt);
+#pragma unroll
+              for (int j = 0; j < Cfg::kMmaSplit; ++j)
+                tma_load_2d(st + Cfg::kA64 + Cfg::kB64 + Cfg::kA32 + j * Cfg::kMmaN * 64, &tm_w32,
+                            &full_bar[stage], tap * CIN + 64, j * Cfg::kMmaN);
+            }
+            if (++stage == Cfg::kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc<kBf16>(128, Cfg::kMmaN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int k_stages = taps * Cfg::kStagesPerTap;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
+      for (int ks = 0; ks < k_stages; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t a64 = st, b64 = st + Cfg::kA64;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t a_desc = make_smem_desc(a64 + k * 32, 16, 1024);
+#pragma unroll
+            for (int j = 0; j < Cfg::kMmaSplit; ++j) {
+              const uint64_t b_desc = make_smem_desc(b64 + j * Cfg::kMmaN * 128 + k * 32, 16, 1024);
+              umma_ss(d_tmem + j * Cfg::kMmaN, a_desc, b_desc, idesc, (ks | k) != 0 ? 1u : 0u);
+            }
+          }
+          if (Cfg::kHas32) {
+            const uint32_t a32 = st + Cfg::kA64 + Cfg::kB64, b32 = a32 + Cfg::kA32;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              // SWIZZLE_64B: 64-byte rows, 8-row groups 512 B apart
+              const uint64_t a_desc = make_smem_desc(a32 + k * 32, 16, 512, 4);
+#pragma unroll
+              for (int j = 0; j < Cfg::kMmaSplit; ++j) {
+                const uint64_t b_desc = make_smem_desc(b32 + j * Cfg::kMmaN * 64 + k * 32, 16, 512, 4);
+                umma_ss(d_tmem + j * Cfg::kMmaN, a_desc, b_desc, idesc, 1u);
+              }
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (ks == k_stages - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == Cfg::kNumAcc) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (thread = output pixel) =====================
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;          // row in tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint16_t* bias = reinterpret_cast<const uint16_t*>(p.bias);
+    const uint16_t* gamma = reinterpret_cast<const uint16_t*>(p.gamma);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int t = tile / tiles_per_frame;
+      const int rem = tile % tiles_per_frame;
+      const int h = (rem / tiles_w) * p.TH + r / p.TW;
+      const int w = (rem % tiles_w) * p.TW + r % p.TW;
+      const bool ok = h < p.H && w < p.W;
+      const long pix = static_cast<long>(h) * p.W + w;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * Cfg::kAccStride;
+
+      if constexpr (N == 16) {
+        // head conv: bias, round, clamp, fp32 NCHW pixels
+        uint32_t v[16];
+        tmem_ld_x16(t_row, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (ok) {
+          for (int c = 0; c < p.cout; ++c) {
+            float x = __uint_as_float(v[c]) + (bias ? load16<kBf16>(bias + c) : 0.f);
+            x = rnd16<kBf16>(x);
+            if (p.out_pix != nullptr) {
+              x = fminf(fmaxf(x, -1.f), 1.f);
+              p.out_pix[(static_cast<long>(t) * p.cout + c) * p.H * p.W + pix] = x;
+            }
+          }
+        }
+      } else {
+        const uint16_t* res = p.residual
+            ? reinterpret_cast<const uint16_t*>(p.residual) + t * p.res_frame + pix * p.res_pix : nullptr;
+        uint16_t* oraw = p.out_raw
+            ? reinterpret_cast<uint16_t*>(p.out_raw) + t * p.raw_frame + pix * p.raw_pix : nullptr;
+        uint16_t* onrm = p.out_norm
+            ? reinterpret_cast<uint16_t*>(p.out_norm) + t * p.norm_frame + pix * p.norm_pix : nullptr;
+        float sumsq = 0.f;
+        // ---- pass 1: bias (+ residual), round, raw store, sum of squares; keep v in TMEM ----
+#pragma unroll 1
+        for (int c = 0; c < N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_x32(t_row + c * 32, v);
+          tmem_ld_wait();
+          if (c == N / 32 - 1 && p.out_norm == nullptr) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (bias != nullptr) {
+            const uint4* b4 = reinterpret_cast<const uint4*>(bias + c * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 bb = __ldg(b4 + q);
+              const uint32_t wv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+              for (int hh = 0; hh < 4; ++hh) {
+                const float2 g = unpack16<kBf16>(wv[hh]);
+                f[q * 8 + hh * 2] += g.x;
+                f[q * 8 + hh * 2 + 1] += g.y;
+              }
+            }
+          }
+          if (res != nullptr && ok) {
+            // reference: y = conv(...) (rounded to 16-bit), out = x + y (rounded)
+            const uint4* r4 = reinterpret_cast<const uint4*>(res + c * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 rr = r4[q];
+              const uint32_t wv[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+              for (int hh = 0; hh < 4; ++hh) {
+                const float2 g = unpack16<kBf16>(wv[hh]);
+                f[q * 8 + hh * 2] = g.x + rnd16<kBf16>(f[q * 8 + hh * 2]);
+                f[q * 8 + hh * 2 + 1] = g.y + rnd16<kBf16>(f[q * 8 + hh * 2 + 1]);
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            f[i] = rnd16<kBf16>(f[i]);
+            sumsq += f[i] * f[i];
+          }
+          if (oraw != nullptr && ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              o.x = pack16<kBf16>(f[q * 8 + 0], f[q * 8 + 1]);
+              o.y = pack16<kBf16>(f[q * 8 + 2], f[q * 8 + 3]);
+              o.z = pack16<kBf16>(f[q * 8 + 4], f[q * 8 + 5]);
+              o.w = pack16<kBf16>(f[q * 8 + 6], f[q * 8 + 7]);
+              reinterpret_cast<uint4*>(oraw + c * 32)[q] = o;
+            }
+          }
+          if (p.out_norm != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(f[i]);
+            tmem_st_x32(t_row + c * 32, v);
+          }
+        }
+        // ---- pass 2: F.normalize(x, dim=C) * sqrt(C) * gamma -> SiLU ----
+        if (p.out_norm != nullptr) {
+          tmem_st_wait();
+          const float nrm = rnd16<kBf16>(sqrtf(sumsq));
+          const float inv = 1.0f / fmaxf(nrm, 1e-30f);
+#pragma unroll 1
+          for (int c = 0; c < N / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_x32(t_row + c * 32, v);
+            tmem_ld_wait();
+            if (c == N / 32 - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            }
+            if (ok) {
+              const uint4* g4 = reinterpret_cast<const uint4*>(gamma + c * 32);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 gg = __ldg(g4 + q);
+                const uint32_t wv[4] = {gg.x, gg.y, gg.z, gg.w};
+                float o[8];
+#pragma unroll
+                for (int hh = 0; hh < 4; ++hh) {
+                  const float2 g = unpack16<kBf16>(wv[hh]);
+                  float a = rnd16<kBf16>(__uint_as_float(v[q * 8 + hh * 2]) * inv);
+                  float b = rnd16<kBf16>(__uint_as_float(v[q * 8 + hh * 2 + 1]) * inv);
+                  a = rnd16<kBf16>(rnd16<kBf16>(a * p.norm_scale) * g.x);
+                  b = rnd16<kBf16>(rnd16<kBf16>(b * p.norm_scale) * g.y);
+                  o[hh * 2] = a / (1.0f + __expf(-a));
+                  o[hh * 2 + 1] = b / (1.0f + __expf(-b));
+                }
+                uint4 ov;
+                ov.x = pack16<kBf16>(o[0], o[1]);
+                ov.y = pack16<kBf16>(o[2], o[3]);
+                ov.z = pack16<kBf16>(o[4], o[5]);
+                ov.w = pack16<kBf16>(o[6], o[7]);
+                reinterpret_cast<uint4*>(onrm + c * 32)[q] = ov;
+              }
+            }
+          }
+        }
+      }
+      if (++acc == Cfg::kNumAcc) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host launcher
+// ---------------------------------------------------------------------------
+template <int CIN, int N, bool kBf16>
+static int launch_conv(const void* in, int t_in, const void* wgt, int w_rows, const ConvParams& p,
+                       cudaStream_t stream) {
+  using Cfg = ConvCfg<CIN, N>;
+  CUtensorMap in64, in32, w64, w32;
+  const uint64_t idims[4] = {static_cast<uint64_t>(CIN), static_cast<uint64_t>(p.W),
+                             static_cast<uint64_t>(p.H), static_cast<uint64_t>(t_in)};
+  const uint64_t istr[3] = {static_cast<uint64_t>(CIN) * 2, static_cast<uint64_t>(p.W) * CIN * 2,
+                            static_cast<uint64_t>(p.H) * p.W * CIN * 2};
+  const uint32_t ibox64[4] = {64, static_cast<uint32_t>(p.TW), static_cast<uint32_t>(p.TH), 1};
+  int rc = make_tmap_nd(&in64, in, 4, idims, istr, ibox64, kBf16, 128);
+  if (rc != KR_OK) return rc;
+  const int taps = p.KT * p.KH * p.KW;
+  const uint64_t wdims[2] = {static_cast<uint64_t>(taps) * CIN, static_cast<uint64_t>(w_rows)};
+  const uint64_t wstr[1] = {static_cast<uint64_t>(taps) * CIN * 2};
+  const uint32_t wbox64[2] = {64, static_cast<uint32_t>(Cfg::kMmaN)};
+  rc = make_tmap_nd(&w64, wgt, 2, wdims, wstr, wbox64, kBf16, 128);
+  if (rc != KR_OK) return rc;
+  in32 = in64;
+  w32 = w64;
+  if (Cfg::kHas32) {
+    const uint32_t ibox32[4] = {32, static_cast<uint32_t>(p.TW), static_cast<uint32_t>(p.TH), 1};
+    rc = make_tmap_nd(&in32, in, 4, idims, istr, ibox32, kBf16, 64);
+    if (rc != KR_OK) return rc;
+    const uint32_t wbox32[2] = {32, static_cast<uint32_t>(Cfg::kMmaN)};
+    rc = make_tmap_nd(&w32, wgt, 2, wdims, wstr, wbox32, kBf16, 64);
+    if (rc != KR_OK) return rc;
+  }
+  auto kern = conv_igemm_kernel<CIN, N, kBf16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_last_error("vae_conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return KR_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int num_tiles = p.T * ((p.W + p.TW - 1) / p.TW) * ((p.H + p.TH - 1) / p.TH);
+  int grid = sm_count();
+  if (grid > num_tiles) grid = num_tiles;
+  kern<<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(in64, in32, w64, w32, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("vae_conv: launch failed: %s", cudaGetErrorString(e));
+    return KR_ERR_CUDA;
+  }
+  return KR_OK;
+}
+
+template <bool kBf16>
+static int dispatch_conv(int cin, int n, const void* in, int t_in, const void* wgt, int w_rows,
+                         const ConvParams& p, cudaStream_t s) {
+#define KR_CONV_CASE(CI, NN) \
+  if (cin == CI && n == NN) return launch_conv<CI, NN, kBf16>(in, t_in, wgt, w_rows, p, s);
+  KR_CONV_CASE(64, 384)
+  KR_CONV_CASE(384, 384)
+  KR_CONV_CASE(192, 384)
+  KR_CONV_CASE(384, 192)
+  KR_CONV_CASE(192, 192)
+  KR_CONV_CASE(192, 96)
+  KR_CONV_CASE(96, 96)
+  KR_CONV_CASE(96, 16)
+#undef KR_CONV_CASE
+  set_last_error("vae_conv: unsupported channel configuration cin=%d n=%d", cin, n);
+  return KR_ERR_UNSUPPORTED_SHAPE;
+}
+
+int vae_conv(int dtype, int cin, int n, const void* in, int t_in, const void* wgt, int w_rows,
+             const ConvParams& p, cudaStream_t stream) {
+  if (p.TW * p.TH != 128 || p.T <= 0 || p.H <= 0 || p.W <= 0) {
+    set_last_error("vae_conv: bad geometry T=%d H=%d W=%d tile=%dx%d", p.T, p.H, p.W, p.TH, p.TW);
+    return KR_ERR_INVALID_ARG;
+  }
+  if ((p.KT != 1 && p.KT != 3) || (p.KH != 1 && p.KH != 3) || (p.KW != 1 && p.KW != 3)) {
+    set_last_error("vae_conv: taps must be 1 or 3");
+    return KR_ERR_INVALID_ARG;
+  }
+  if (t_in < p.T + p.KT - 1) {
+    set_last_error("vae_conv: input holds %d frames, needs %d", t_in, p.T + p.KT - 1);
+    return KR_ERR_INVALID_ARG;
+  }
+  if (p.out_norm != nullptr && p.gamma == nullptr) {
+    set_last_error("vae_conv: normalised output needs gamma");
+    return KR_ERR_INVALID_ARG;
+  }
+  return dtype == 0 ? dispatch_conv<true>(cin, n, in, t_in, wgt, w_rows, p, stream)
+                    : dispatch_conv<false>(cin, n, in, t_in, wgt, w_rows, p, stream);
+}
+
+// ---------------------------------------------------------------------------
+// RMS_norm (per pixel over C) * sqrt(C) * gamma -> optional SiLU; channels-last rows.
+// One warp per pixel.  (vae.py:39-54; used where the producer is not a conv epilogue.)
+// ---------------------------------------------------------------------------
+template <bool kBf16>
+__global__ void rmsnorm_silu_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y,
+                                    const uint16_t* __restrict__ gamma, long pixels, int C,
+                                    float scale, int do_silu) {
+  const long pix = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pix >= pixels) return;
+  const int lane = threadIdx.x & 31;
+  const uint16_t* xr = x + pix * C;
+  float v[12];   // C <= 384 -> 12 values per lane
+  float ss = 0.f;
+  int n = 0;
+  for (int c = lane; c < C; c += 32) {
+    v[n] = load16<kBf16>(xr + c);
+    ss += v[n] * v[n];
+    ++n;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float nrm = rnd16<kBf16>(sqrtf(ss));
+  const float inv = 1.0f / fmaxf(nrm, 1e-30f);
+  uint16_t* yr = y + pix * C;
+  n = 0;
+  for (int c = lane; c < C; c += 32) {
+    float a = rnd16<kBf16>(v[n] * inv);
+    a = rnd16<kBf16>(rnd16<kBf16>(a * scale) * load16<kBf16>(gamma + c));
+    if (do_silu) a = a / (1.0f + __expf(-a));
+    const uint32_t pk = pack16<kBf16>(a, 0.f);
+    yr[c] = static_cast<uint16_t>(pk & 0xffff);
+    ++n;
+  }
+}
+
+int vae_rmsnorm_silu(int dtype, const void* x, void* y, const void* gamma, long pixels, int C,
+                     int do_silu, cudaStream_t stream) {
+  if (C > 384 || C <= 0 || pixels <= 0) {
+    set_last_error("vae_rmsnorm_silu: unsupported C=%d", C);
+    return KR_ERR_UNSUPPORTED_SHAPE;
+  }
+  const int wpb = 8;
+  const unsigned grid = static_cast<unsigned>((pixels + wpb - 1) / wpb);
+  const float scale = sqrtf(static_cast<float>(C));
+  if (dtype == 0)
+    rmsnorm_silu_kernel<true><<<grid, wpb * 32, 0, stream>>>(
+        static_cast<const uint16_t*>(x), static_cast<uint16_t*>(y),
+        static_cast<const uint16_t*>(gamma), pixels, C, scale, do_silu);
+  else
+    rmsnorm_silu_kernel<false><<<grid, wpb * 32, 0, stream>>>(
+        static_cast<const uint16_t*>(x), static_cast<uint16_t*>(y),
+        static_cast<const uint16_t*>(gamma), pixels, C, scale, do_silu);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("vae_rmsnorm_silu: launch failed: %s", cudaGetErrorString(e));
+    return KR_ERR_CUDA;
+  }
+  return KR_OK;
+}
+
+// ---------------------------------------------------------------------------
+// nearest 2x spatial upsample, channels-last: in [T, H, W, C] -> out [T, 2H, 2W, C]
+// (vae.py:57-63 casts to fp32 and back: an exact copy)
+// ---------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int T, int H,
+                                  int W, int C8) {
+  const long total = static_cast<long>(T) * 4 * H * W * C8;
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = idx % C8;
+  long r = idx / C8;
+  const int w2 = r % (2 * W);
+  r /= (2 * W);
+  const int h2 = r % (2 * H);
+  const int t = r / (2 * H);
+  out[idx] = in[((static_cast<long>(t) * H + (h2 >> 1)) * W + (w2 >> 1)) * C8 + c];
+}
+
+int vae_upsample2x(const void* in, void* out, int T, int H, int W, int C, cudaStream_t stream) {
+  if (C % 8 != 0) {
+    set_last_error("vae_upsample2x: C=%d not a multiple of 8", C);
+    return KR_ERR_UNSUPPORTED_SHAPE;
+  }
+  const long total = static_cast<long>(T) * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      static_cast<const uint4*>(in), static_cast<uint4*>(out), T, H, W, C / 8);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("vae_upsample2x: launch failed: %s", cudaGetErrorString(e));
+    return KR_ERR_CUDA;
+  }
+  return KR_OK;
+}
+
+// ---------------------------------------------------------------------------
+// latent un-scaling + conv2 (1x1x1, 16 -> 16) + NCHW -> channels-last padded to 64 channels
+//   z [T, 16, H, W] (strided) ; x = z / inv_std + mean ; y = W2 x + b2   (vae_block3.py:205-214)
+//   out [T, H, W, 64] (channels >= 16 zero) feeds conv1 whose weights are zero-padded likewise.
+// ---------------------------------------------------------------------------
+template <bool kBf16>
+__global__ void scale_input_kernel(const uint16_t* __restrict__ z, long zt, long zc, long zh, long zw,
+                                   const uint16_t* __restrict__ mean, const uint16_t* __restrict__ inv_std,
+                                   const uint16_t* __restrict__ w2, const uint16_t* __restrict__ b2,
+                                   uint16_t* __restrict__ out, int T, int H, int W) {
+  const long total = static_cast<long>(T) * H * W;
+  const long pix = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const int w = pix % W, h = (pix / W) % H, t = pix / (static_cast<long>(W) * H);
+  float x[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const float zv = load16<kBf16>(z + t * zt + c * zc + h * zh + w * zw);
+    // z / scale[1] + scale[0], each op rounded to the 16-bit dtype
+    x[c] = rnd16<kBf16>(rnd16<kBf16>(zv / load16<kBf16>(inv_std + c)) + load16<kBf16>(mean + c));
+  }
+  uint32_t o[32];
+#pragma unroll
+  for (int n = 0; n < 16; n += 2) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      a += load16<kBf16>(w2 + n * 16 + c) * x[c];
+      b += load16<kBf16>(w2 + (n + 1) * 16 + c) * x[c];
+    }
+    a += load16<kBf16>(b2 + n);
+    b += load16<kBf16>(b2 + n + 1);
+    o[n / 2] = pack16<kBf16>(a, b);
+  }
+#pragma unroll
+  for (int i = 8; i < 32; ++i) o[i] = 0u;
+  uint4* op = reinterpret_cast<uint4*>(out + pix * 64);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) op[q] = make_uint4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+}
+
+int vae_scale_input(int dtype, const void* z, long zt, long zc, long zh, long zw, const void* mean,
+                    const void* inv_std, const void* w2, const void* b2, void* out, int T, int H,
+                    int W, cudaStream_t stream) {
+  const long total = static_cast<long>(T) * H * W;
+  const unsigned grid = static_cast<unsigned>((total + 127) / 128);
+  if (dtype == 0)
+    scale_input_kernel<true><<<grid, 128, 0, stream>>>(
+        static_cast<const uint16_t*>(z), zt, zc, zh, zw, static_cast<const uint16_t*>(mean),
+        static_cast<const uint16_t*>(inv_std), static_cast<const uint16_t*>(w2),
+        static_cast<const uint16_t*>(b2), static_cast<uint16_t*>(out), T, H, W);
+  else
+    scale_input_kernel<false><<<grid, 128, 0, stream>>>(
+        static_cast<const uint16_t*>(z), zt, zc, zh, zw, static_cast<const uint16_t*>(mean),
+        static_cast<const uint16_t*>(inv_std), static_cast<const uint16_t*>(w2),
+        static_cast<const uint16_t*>(b2), static_cast<uint16_t*>(out), T, H, W);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("vae_scale_input: launch failed: %s", cudaGetErrorString(e));
+    return KR_ERR_CUDA;
+  }
+  return KR_OK;
+}
+
+// ---------------------------------------------------------------------------
+// row softmax: fp32 scores [rows, ld] (first `cols` valid) -> 16-bit probabilities [rows, ldo]
+// (middle AttentionBlock, vae.py:239-244).  One CTA per row.
+// ---------------------------------------------------------------------------
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ s, long ld, uint16_t* __restrict__ pout, long ldo,
+                    int cols) {
+  __shared__ float red[8];
+  const float* sr = s + static_cast<long>(blockIdx.x) * ld;
+  uint16_t* pr = pout + static_cast<long>(blockIdx.x) * ldo;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += 256) m = fmaxf(m, sr[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < cols; c += 256) sum += __expf(sr[c] - m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+  for (int c = threadIdx.x; c < cols; c += 256) {
+    const uint32_t pk = pack16<kBf16>(__expf(sr[c] - m) * inv, 0.f);
+    pr[c] = static_cast<uint16_t>(pk & 0xffff);
+  }
+}
+
+int softmax_rows(int dtype, const float* s, long ld, void* pout, long ldo, int rows, int cols,
+                 cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) {
+    set_last_error("softmax_rows: empty input");
+    return KR_ERR_INVALID_ARG;
+  }
+  if (dtype == 0)
+    softmax_rows_kernel<true><<<rows, 256, 0, stream>>>(s, ld, static_cast<uint16_t*>(pout), ldo, cols);
+  else
+    softmax_rows_kernel<false><<<rows, 256, 0, stream>>>(s, ld, static_cast<uint16_t*>(pout), ldo, cols);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("softmax_rows: launch failed: %s", cudaGetErrorString(e));
+    return KR_ERR_CUDA;
+  }
+  return KR_OK;
+}
+
+}  // namespace kr

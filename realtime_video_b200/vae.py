@@ -1,0 +1,457 @@
+"""Causal 3D VAE decoder on the B200 kernels — host-side mirror of the reference's decoder.
+
+Mirrors ``demo_utils/vae_block3.py`` (VAEDecoderWrapper :177-230, VAEDecoder3d :334-443) and the
+layers of ``wan/modules/vae.py`` it is built from (CausalConv3d :17, RMS_norm :39, Resample :66,
+ResidualBlock :175, AttentionBlock :212): same module tree / state-dict keys (``decoder.*``,
+``conv2.*``), so the reference's ``load_state_dict`` of the Wan2.1 VAE checkpoint works.
+The modules only HOLD parameters; ``DecoderEngine`` runs the arithmetic as a fixed schedule of
+implicit-GEMM convolutions with fused epilogues (``ops.vae_conv``) on channels-last activations.
+
+Cache semantics (reference vae.py:191-206, vae_block3.py:46-91):
+  * every 3x3x3 conv keeps the last two frames of its INPUT; here each conv owns a persistent
+    input buffer [2 + T, H, W, C] whose two leading frames are that cache (read in place);
+  * a zero cache is exactly the reference's zero padding for the first chunk;
+  * up3d ``Resample``: the very first latent frame skips ``time_conv`` and leaves a ZERO cache
+    (sentinel, vae_block3.py:51-53); one-frame chunks then update the cache as
+    [where(old_last == 0, 0, x), x] (vae_block3.py:56-60) — reproduced verbatim.
+Latent frames of one call are processed together per layer (one launch per conv), which is
+arithmetically identical to the reference's frame-by-frame loop because every conv is causal.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+MEAN = [-0.7571, -0.7089, -0.9113, 0.1075, -0.1745, 0.9653, -0.1517, 1.5508,
+        0.4134, -0.0715, 0.5517, -0.3632, -0.1922, -0.9497, 0.2503, -0.2921]
+STD = [2.8184, 1.4541, 2.3275, 2.6558, 1.2196, 1.7708, 2.6052, 2.0743,
+       3.2687, 2.1526, 2.8652, 1.5579, 1.6382, 1.1253, 2.8251, 1.9160]
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter holders (same attribute names / state-dict keys as the reference modules)
+# ---------------------------------------------------------------------------------------------
+class CausalConv3d(nn.Conv3d):
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._padding = (self.padding[2], self.padding[2], self.padding[1], self.padding[1],
+                         2 * self.padding[0], 0)
+        self.padding = (0, 0, 0)
+
+
+class RMS_norm(nn.Module):
+    def __init__(self, dim, channel_first=True, images=True, bias=False):
+        super().__init__()
+        bdims = (1, 1, 1) if not images else (1, 1)
+        self.channel_first, self.scale = channel_first, dim ** 0.5
+        self.gamma = nn.Parameter(torch.ones((dim, *bdims) if channel_first else (dim,)))
+        self.bias = nn.Parameter(torch.zeros((dim, *bdims))) if bias else 0.
+
+
+class Upsample(nn.Upsample):
+    pass
+
+
+class Resample(nn.Module):
+    def __init__(self, dim, mode):
+        assert mode in ("upsample2d", "upsample3d")
+        super().__init__()
+        self.dim, self.mode, self.cache_t = dim, mode, 2
+        self.resample = nn.Sequential(Upsample(scale_factor=(2., 2.), mode="nearest"),
+                                      nn.Conv2d(dim, dim // 2, 3, padding=1))
+        if mode == "upsample3d":
+            self.time_conv = CausalConv3d(dim, dim * 2, (3, 1, 1), padding=(1, 0, 0))
+
+
+class ResidualBlock(nn.Module):
+    def __init__(self, in_dim, out_dim, dropout=0.0):
+        super().__init__()
+        self.in_dim, self.out_dim = in_dim, out_dim
+        self.residual = nn.Sequential(
+            RMS_norm(in_dim, images=False), nn.SiLU(), CausalConv3d(in_dim, out_dim, 3, padding=1),
+            RMS_norm(out_dim, images=False), nn.SiLU(), nn.Dropout(dropout),
+            CausalConv3d(out_dim, out_dim, 3, padding=1))
+        self.shortcut = CausalConv3d(in_dim, out_dim, 1) if in_dim != out_dim else nn.Identity()
+
+
+class AttentionBlock(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+        self.norm = RMS_norm(dim)
+        self.to_qkv = nn.Conv2d(dim, dim * 3, 1)
+        self.proj = nn.Conv2d(dim, dim, 1)
+        nn.init.zeros_(self.proj.weight)
+
+
+class VAEDecoder3d(nn.Module):
+    """demo_utils/vae_block3.py:334-385 (module tree only)."""
+
+    def __init__(self, dim=96, z_dim=16, dim_mult=[1, 2, 4, 4], num_res_blocks=2, attn_scales=[],
+                 temperal_upsample=[True, True, False], dropout=0.0):
+        super().__init__()
+        if attn_scales:
+            raise NotImplementedError("attn_scales is empty in every Wan 2.1 VAE")
+        self.dim, self.z_dim, self.dim_mult, self.num_res_blocks = dim, z_dim, dim_mult, num_res_blocks
+        self.temperal_upsample = temperal_upsample
+        self.cache_t, self.decoder_conv_num = 2, 32
+        dims = [dim * u for u in [dim_mult[-1]] + dim_mult[::-1]]
+        self.conv1 = CausalConv3d(z_dim, dims[0], 3, padding=1)
+        self.middle = nn.Sequential(ResidualBlock(dims[0], dims[0], dropout), AttentionBlock(dims[0]),
+                                    ResidualBlock(dims[0], dims[0], dropout))
+        ups = []
+        for i, (in_dim, out_dim) in enumerate(zip(dims[:-1], dims[1:])):
+            if i in (1, 2, 3):
+                in_dim = in_dim // 2
+            for _ in range(num_res_blocks + 1):
+                ups.append(ResidualBlock(in_dim, out_dim, dropout))
+                in_dim = out_dim
+            if i != len(dim_mult) - 1:
+                ups.append(Resample(out_dim, mode="upsample3d" if temperal_upsample[i] else "upsample2d"))
+        self.upsamples = nn.Sequential(*ups)
+        self.head = nn.Sequential(RMS_norm(out_dim, images=False), nn.SiLU(),
+                                  CausalConv3d(out_dim, 3, 3, padding=1))
+
+
+# ---------------------------------------------------------------------------------------------
+# engine
+# ---------------------------------------------------------------------------------------------
+def _tile_for(H: int, W: int):
+    """(tile_w, tile_h) with tile_w*tile_h == 128 minimising padded area."""
+    best = None
+    for tw in (4, 8, 16, 32, 64):
+        th = 128 // tw
+        area = math.ceil(W / tw) * tw * math.ceil(H / th) * th
+        if best is None or area < best[0] or (area == best[0] and abs(tw - 16) < abs(best[1] - 16)):
+            best = (area, tw, th)
+    return best[1], best[2]
+
+
+class _Conv:
+    """Kernel-ready conv: weight [rows, taps*cin_pad], bias [n], taps, channel config, and (for
+    temporal convs) the persistent input buffer whose two leading frames are the cache."""
+
+    def __init__(self, weight, bias, cin_pad, n_pad, cout, taps):
+        self.weight, self.bias = weight, bias
+        self.cin, self.n, self.cout, self.taps = cin_pad, n_pad, cout, taps
+        self.buf: Optional[torch.Tensor] = None     # [kt-1 + Tmax, H, W, cin]
+
+
+def _prep_conv(w: torch.Tensor, b: torch.Tensor, dtype, device, cin_pad=None, n_pad=None) -> _Conv:
+    if w.dim() == 4:                       # Conv2d [Cout, Cin, kh, kw] -> kt = 1
+        w = w.unsqueeze(2)
+    cout, cin, kt, kh, kw = w.shape
+    cin_pad = cin_pad or cin
+    n_pad = n_pad or cout
+    wp = torch.zeros(n_pad, kt, kh, kw, cin_pad, dtype=dtype, device=device)
+    wp[:cout, :, :, :, :cin] = w.to(device=device, dtype=dtype).permute(0, 2, 3, 4, 1)
+    bp = torch.zeros(max(n_pad, 32), dtype=dtype, device=device)
+    bp[:cout] = b.to(device=device, dtype=dtype)
+    return _Conv(wp.reshape(n_pad, kt * kh * kw * cin_pad).contiguous(), bp, cin_pad, n_pad, cout, (kt, kh, kw))
+
+
+class DecoderEngine:
+    """Runs VAEDecoder3d (+ the wrapper's un-scale and conv2) on the sm_100a kernels."""
+
+    MAX_CHUNK = 3          # latent frames per launch sequence
+
+    def __init__(self, decoder: VAEDecoder3d, conv2: nn.Module, mean: torch.Tensor, std: torch.Tensor):
+        self.decoder, self.conv2, self.mean, self.std = decoder, conv2, mean, std
+        self._key = None
+        self.H = self.W = None
+
+    # -- weight preparation ---------------------------------------------------------------
+    def _prepare(self, dtype, device, H, W):
+        key = (dtype, str(device), H, W, self.decoder.conv1.weight._version, self.decoder.conv1.weight.data_ptr())
+        if self._key == key:
+            return
+        d = self.decoder
+        pc = lambda m, **kw: _prep_conv(m.weight.data, m.bias.data, dtype, device, **kw)  # noqa: E731
+        g = lambda n: n.gamma.data.reshape(-1).to(device=device, dtype=dtype).contiguous()  # noqa: E731
+        self.dtype, self.device, self.H, self.W = dtype, device, H, W
+        self.mean_d = self.mean.to(device=device, dtype=dtype)
+        self.inv_std_d = (1.0 / self.std.to(device=device, dtype=dtype))
+        self.w2 = self.conv2.weight.data.reshape(16, 16).to(device=device, dtype=dtype).contiguous()
+        self.b2 = self.conv2.bias.data.to(device=device, dtype=dtype).contiguous()
+        self.conv1 = pc(d.conv1, cin_pad=64)
+        self.stages = []       # flat op list
+        blocks = list(d.middle) + list(d.upsamples)
+        self.blocks = []
+        for m in blocks:
+            if isinstance(m, ResidualBlock):
+                r = m.residual
+                self.blocks.append(dict(kind="res", g1=g(r[0]), c1=pc(r[2]), g2=g(r[3]), c2=pc(r[6]),
+                                        sc=pc(m.shortcut) if isinstance(m.shortcut, nn.Conv3d) else None,
+                                        cin=m.in_dim, cout=m.out_dim))
+            elif isinstance(m, AttentionBlock):
+                C = m.dim
+                wqkv = m.to_qkv.weight.data.reshape(3 * C, C).to(device=device, dtype=dtype).contiguous()
+                bqkv = m.to_qkv.bias.data.to(device=device, dtype=dtype).contiguous()
+                self.blocks.append(dict(kind="attn", g=g(m.norm), wqkv=wqkv, bqkv=bqkv, C=C,
+                                        wproj=m.proj.weight.data.reshape(C, C).to(device=device, dtype=dtype).contiguous(),
+                                        bproj=m.proj.bias.data.to(device=device, dtype=dtype).contiguous()))
+            elif isinstance(m, Resample):
+                e = dict(kind="up", mode=m.mode, C=m.dim, conv=pc(m.resample[1]))
+                if m.mode == "upsample3d":
+                    e["tconv"] = pc(m.time_conv)
+                    e["tcache"] = None
+                self.blocks.append(e)
+        self.g_head = g(d.head[0])
+        self.head = pc(d.head[2], n_pad=16)
+        self._key = key
+        self._alloc(H, W)
+
+    def _alloc(self, H, W):
+        """Persistent conv-input buffers (cache frames in front) for a chunk of MAX_CHUNK latent
+        frames; spatial size doubles at every Resample, frames double at every up3d."""
+        dt, dev = self.dtype, self.device
+        T = self.MAX_CHUNK
+
+        def buf(conv: _Conv, t, h, w):
+            conv.buf = torch.zeros(conv.taps[0] - 1 + t, h, w, conv.cin, dtype=dt, device=dev)
+
+        buf(self.conv1, T, H, W)
+        h, w, t = H, W, T
+        for b in self.blocks:
+            if b["kind"] == "res":
+                buf(b["c1"], t, h, w)
+                buf(b["c2"], t, h, w)
+            elif b["kind"] == "up":
+                if b["mode"] == "upsample3d":
+                    b["tcache"] = torch.zeros(2, h, w, b["C"], dtype=dt, device=dev)
+                    t *= 2
+                h, w = 2 * h, 2 * w
+        buf(self.head, t, h, w)
+        self.initialised = False       # no frame decoded yet (first-frame sentinel state)
+
+    def reset(self):
+        """Forget the stream: zero caches, first-frame state."""
+        self.conv1.buf.zero_()
+        for b in self.blocks:
+            if b["kind"] == "res":
+                b["c1"].buf.zero_()
+                b["c2"].buf.zero_()
+            elif b["kind"] == "up" and b["mode"] == "upsample3d":
+                b["tcache"].zero_()
+        self.head.buf.zero_()
+        self.initialised = False
+
+    # -- cache export / import (opaque to the caller, tensors so that .to() works) -----------
+    def export_cache(self) -> List[Optional[torch.Tensor]]:
+        out: List[Optional[torch.Tensor]] = [None] * 55
+        out[0] = self.conv1.buf[:2]
+        i = 1
+        for b in self.blocks:
+            if b["kind"] == "res":
+                out[i], out[i + 1] = b["c1"].buf[:2], b["c2"].buf[:2]
+                i += 2
+            elif b["kind"] == "up" and b["mode"] == "upsample3d":
+                out[i] = b["tcache"]
+                i += 1
+        out[i] = self.head.buf[:2]
+        return out
+
+    def import_cache(self, cache: List[Optional[torch.Tensor]]):
+        if cache is None or all(c is None for c in cache):
+            self.reset()
+            return
+        mine = self.export_cache()
+        for src, dst in zip(cache, mine):
+            if dst is None:
+                continue
+            if src is None:
+                raise ValueError("partial VAE feature cache: pass back the list this decoder returned")
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src.reshape(dst.shape))
+        self.initialised = True
+
+    # -- one conv with fused epilogue --------------------------------------------------------
+    def _conv(self, c: _Conv, T, src: Optional[torch.Tensor] = None, **kw):
+        x = c.buf if src is None else src
+        H, W = x.shape[1], x.shape[2]
+        ops.vae_conv(x, c.weight, c.bias, n=c.n, cout=c.cout, T=T, taps=c.taps, tile=_tile_for(H, W), **kw)
+        if src is None and c.taps[0] == 3:
+            tail = c.buf[T:T + 2]                  # roll: last two input frames become the cache
+            c.buf[:2].copy_(tail.clone() if T < 2 else tail)
+
+    def _new(self, t, h, w, c):
+        return torch.empty(t, h, w, c, dtype=self.dtype, device=self.device)
+
+    def _attention(self, b, x):
+        """vae.py:229-251 — per frame single-head attention over H*W tokens, C channels."""
+        T, H, W, C = x.shape
+        L = H * W
+        if L % 32 != 0:
+            raise NotImplementedError(f"VAE attention: H*W={L} must be a multiple of 32")
+        out = torch.empty_like(x)
+        xn = ops.vae_rmsnorm_silu(x, b["g"], torch.empty_like(x), silu=False)
+        for t in range(T):
+            xt, xnt = x[t].view(L, C), xn[t].view(L, C)
+            qkv = ops.gemm(xnt, b["wqkv"], b["bqkv"])
+            q, k = qkv[:, :C], qkv[:, C:2 * C]
+            s = ops.gemm(q, k, None, epilogue=ops.EPI_F32, alpha=1.0 / math.sqrt(C))      # [L, L] fp32
+            p = ops.softmax_rows(s, torch.empty(L, L, dtype=x.dtype, device=x.device))
+            vt = ops.gemm(b["wqkv"][2 * C:], xnt, None)                                       # V^T [C, L]
+            o = ops.gemm(p, vt, b["bqkv"][2 * C:])       # softmax rows sum to 1: P(V + 1 b^T) = PV + b^T
+            ops.gemm(o, b["wproj"], b["bproj"], epilogue=ops.EPI_BIAS_RES, residual=xt, out=out[t].view(L, C))
+        return out
+
+    # -- decode a chunk of latent frames -----------------------------------------------------
+    def decode_chunk(self, z: torch.Tensor, first: bool) -> torch.Tensor:
+        """z [T0, 16, h, w] (strided ok) -> pixels [T', 3, 8h, 8w] fp32 in [-1, 1];
+        T' = 1 for the first-ever latent frame (first=True requires T0 == 1), else 4*T0."""
+        T = z.shape[0]
+        assert T <= self.MAX_CHUNK and (not first or T == 1)
+        c1 = self.conv1
+        ops.vae_scale_input(z, self.mean_d, self.inv_std_d, self.w2, self.b2, c1.buf[2:2 + T])
+        blocks = self.blocks
+        h, w = self.H, self.W
+
+        def next_gamma(i):
+            """gamma of the norm that consumes block i's output (next ResidualBlock / head)."""
+            if i + 1 < len(blocks):
+                nb = blocks[i + 1]
+                return (nb["g1"], nb["c1"]) if nb["kind"] == "res" else (None, None)
+            return self.g_head, self.head
+
+        # conv1 -> raw x (residual stream) + normalised input of middle.0.conv1
+        x = self._new(T, h, w, c1.cout)
+        g, nxt = blocks[0]["g1"], blocks[0]["c1"]
+        self._conv(c1, T, out_raw=x, out_norm=nxt.buf[2:2 + T], gamma=g)
+
+        for i, b in enumerate(blocks):
+            if b["kind"] == "res":
+                ca, cb = b["c1"], b["c2"]
+                res = x
+                if b["sc"] is not None:
+                    res = self._new(T, h, w, b["cout"])
+                    self._conv(b["sc"], T, src=x, out_raw=res)
+                self._conv(ca, T, out_norm=cb.buf[2:2 + T], gamma=b["g2"])
+                g, nxt = next_gamma(i)
+                need_raw = nxt is not self.head          # the head only needs the normalised tensor
+                xo = self._new(T, h, w, b["cout"]) if need_raw else None
+                self._conv(cb, T, residual=res, out_raw=xo,
+                           out_norm=nxt.buf[2:2 + T] if g is not None else None, gamma=g)
+                x = xo
+            elif b["kind"] == "attn":
+                x = self._attention(b, x)
+                nb = blocks[i + 1]
+                ops.vae_rmsnorm_silu(x, nb["g1"], nb["c1"].buf[2:2 + T])
+            else:  # Resample
+                C = b["C"]
+                if b["mode"] == "upsample3d":
+                    if first:
+                        b["tcache"].zero_()                    # sentinel, time_conv skipped
+                    else:
+                        tc = b["tconv"]
+                        y = self._new(2 * T, h, w, C)
+                        frame = h * w * C
+                        if True:
+                            # chunk-wise cache update of vae_block3.py:55-62 per reference chunk
+                            step = self._chunk_frames(i)
+                            for s0 in range(0, T, step):
+                                xin = torch.cat([b["tcache"], x[s0:s0 + step]], dim=0)
+                                for half in range(2):
+                                    ops.vae_conv(xin, tc.weight[half * C:(half + 1) * C], tc.bias[half * C:],
+                                                 n=C, cout=C, T=step, taps=tc.taps, tile=_tile_for(h, w),
+                                                 out_raw=y[2 * s0 + half:], raw_frame_stride=2 * frame)
+                                xs = x[s0:s0 + step]
+                                if step >= 2:
+                                    b["tcache"].copy_(xs[-2:])
+                                else:
+                                    old_last = b["tcache"][1]
+                                    pad = torch.where(old_last == 0, torch.zeros_like(xs[0]), xs[0])
+                                    b["tcache"][0].copy_(pad)
+                                    b["tcache"][1].copy_(xs[0])
+                        x, T = y, 2 * T
+                up = ops.vae_upsample2x(x, self._new(T, 2 * h, 2 * w, C))
+                h, w = 2 * h, 2 * w
+                cv = b["conv"]
+                x = self._new(T, h, w, cv.cout)
+                g, nxt = next_gamma(i)
+                self._conv(cv, T, src=up, out_raw=x, out_norm=nxt.buf[2:2 + T], gamma=g)
+        # head conv -> clamped fp32 pixels [T, 3, H, W]
+        pix = torch.empty(T, 3, h, w, dtype=torch.float32, device=self.device)
+        self._conv(self.head, T, out_pix=pix)
+        self.initialised = True
+        return pix
+
+    def _chunk_frames(self, block_index: int) -> int:
+        """Frames per REFERENCE chunk (one latent frame) at the input of Resample `block_index`:
+        1 before the first up3d, 2 before the second."""
+        n = 1
+        for b in self.blocks[:block_index]:
+            if b["kind"] == "up" and b["mode"] == "upsample3d":
+                n *= 2
+        return n
+
+    def decode(self, z: torch.Tensor, feat_cache: List[Optional[torch.Tensor]]):
+        """z [1, T, 16, h, w] -> (pixels [1, T', 3, 8h, 8w] fp32, feat_cache list)."""
+        assert z.shape[0] == 1, "batch size 1 (reference: release_server.py:404)"
+        zt = z[0]
+        dtype = zt.dtype if zt.dtype in (torch.float16, torch.bfloat16) else torch.float16
+        self._prepare(dtype, zt.device, zt.shape[-2], zt.shape[-1])
+        self.import_cache(feat_cache)
+        zt = zt.to(dtype)
+        outs = []
+        i = 0
+        if not self.initialised:
+            outs.append(self.decode_chunk(zt[0:1], first=True))
+            i = 1
+        while i < zt.shape[0]:
+            n = min(self.MAX_CHUNK, zt.shape[0] - i)
+            outs.append(self.decode_chunk(zt[i:i + n], first=False))
+            i += n
+        pix = torch.cat(outs, dim=0) if len(outs) > 1 else outs[0]
+        return pix[None], self.export_cache()
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference-facing wrappers
+# ---------------------------------------------------------------------------------------------
+class VAEDecoderWrapper(nn.Module):
+    """demo_utils/vae_block3.py:177-230: ``forward(z[1,T,16,h,w], *feat_cache) ->
+    (pixels [1,T',3,H,W] fp32 in [-1,1], feat_cache)``.  The cache list entries are this
+    implementation's channels-last buffers (opaque to the caller, which only passes them back)."""
+
+    def __init__(self):
+        super().__init__()
+        self.decoder = VAEDecoder3d()
+        self.register_buffer("mean", torch.tensor(MEAN, dtype=torch.float32))
+        self.register_buffer("std", torch.tensor(STD, dtype=torch.float32))
+        self.z_dim = 16
+        self.conv2 = CausalConv3d(self.z_dim, self.z_dim, 1)
+        self._engine: Optional[DecoderEngine] = None
+
+    @property
+    def engine(self) -> DecoderEngine:
+        if self._engine is None:
+            self._engine = DecoderEngine(self.decoder, self.conv2, self.mean, self.std)
+        return self._engine
+
+    def _apply(self, fn, *a, **k):     # .to() / .half() invalidate prepared weights
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def forward(self, z: torch.Tensor, *feat_cache):
+        eng = self.engine
+        eng.mean, eng.std = self.mean, self.std
+        return eng.decode(z, list(feat_cache))
+
+
+class WanVAEDecoderCore:
+    """Decoder used by the classic-path ``WanVAEWrapper`` (utils/wan_wrapper.py:58-118)."""
+    MEAN, STD = MEAN, STD
+
+    def __init__(self, wrapper: Optional[VAEDecoderWrapper] = None):
+        self.wrapper = wrapper if wrapper is not None else VAEDecoderWrapper()
+        self.num_cache_slots = 55
+        self.persistent_cache: List[Optional[torch.Tensor]] = [None] * 55
+
+    def decode(self, latent, cache):
+        return self.wrapper(latent, *cache)

@@ -1,0 +1,51 @@
+"""Generate VAE-decoder golden vectors by running the UNMODIFIED reference
+``demo_utils.vae_block3.VAEDecoderWrapper`` on CPU in fp32 (build container only).
+
+    python tests/golden/make_vae_goldens.py        # writes tests/golden/vae_small.npz
+
+Weights are NOT stored: both sides rebuild them from ``oracle.vae_oracle.synthetic_vae_params``
+(one generator per tensor, seeded by the state-dict key), so the fixture holds only the latents
+and the reference's outputs.  Cases, latent 8x12 (-> 64x96 pixels) and 16x24 (-> 128x192):
+  call 1: 3 latent frames with an empty cache (first-frame path: 1 + 4 + 4 = 9 frames)
+  call 2: 3 latent frames with the returned cache (12 frames)
+  call 3: 1 latent frame (4 frames) — single-frame chunk, exercises the `where` cache update
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE))
+sys.path.insert(0, str(HERE.parent.parent))
+import ref_shim  # noqa: E402
+from oracle.vae_oracle import synthetic_vae_params  # noqa: E402
+
+OUT = {}
+
+
+@torch.no_grad()
+def run(tag, h, w, sub):
+    ns = ref_shim.install()
+    m = ns.vae_block3.VAEDecoderWrapper()
+    sd = synthetic_vae_params(seed=0)
+    missing = m.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys and set(missing.missing_keys) <= {"mean", "std"}, missing
+    m = m.float().eval()
+    g = torch.Generator().manual_seed(11)
+    cache = [None] * 55
+    for call, t in enumerate((3, 3, 1)):
+        z = torch.randn(1, t, 16, h, w, generator=g)
+        OUT[f"{tag}/z{call}"] = z.numpy()
+        px, cache = m(z, *cache)
+        OUT[f"{tag}/px{call}"] = px[..., ::sub, ::sub].contiguous().numpy()
+        print(tag, call, tuple(px.shape), float(px.abs().mean()), flush=True)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    run("s8x12", 8, 12, 1)
+    run("s16x24", 16, 24, 2)
+    np.savez_compressed(HERE / "vae_small.npz", **OUT)
+    print("vae_small.npz", sum(v.nbytes for v in OUT.values()) / 1e6, "MB raw")
