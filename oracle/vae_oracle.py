@@ -132,66 +132,4 @@ class VAEDecoderOracle:
         return out.permute(0, 2, 1, 3, 4), cache
 
 
-def synthetic_vae_params(seed: int = 0, dim: int = 96, z_dim: int = 16):
-    """Deterministic decoder weights independent of module construction order: every tensor is
-    drawn from its own generator seeded by (seed, key).  Conv weights ~ N(0, 1/fan_in) * 1.4,
-    biases ~ N(0, .02), gammas ~ 1 + N(0, .1)."""
-    import zlib
-    shapes = {}
-    dims = [dim * 4, dim * 4, dim * 4, dim * 2, dim]
-
-    def conv3(name, ci, co, k):
-        shapes[name + ".weight"] = (co, ci, *k)
-        shapes[name + ".bias"] = (co,)
-
-    def res(pre, ci, co):
-        shapes[pre + ".residual.0.gamma"] = (ci, 1, 1, 1)
-        conv3(pre + ".residual.2", ci, co, (3, 3, 3))
-        shapes[pre + ".residual.3.gamma"] = (co, 1, 1, 1)
-        conv3(pre + ".residual.6", co, co, (3, 3, 3))
-        if ci != co:
-            conv3(pre + ".shortcut", ci, co, (1, 1, 1))
-
-    conv3("conv2", z_dim, z_dim, (1, 1, 1))
-    conv3("decoder.conv1", z_dim, dims[0], (3, 3, 3))
-    res("decoder.middle.0", dims[0], dims[0])
-    shapes["decoder.middle.1.norm.gamma"] = (dims[0], 1, 1)
-    shapes["decoder.middle.1.to_qkv.weight"] = (3 * dims[0], dims[0], 1, 1)
-    shapes["decoder.middle.1.to_qkv.bias"] = (3 * dims[0],)
-    shapes["decoder.middle.1.proj.weight"] = (dims[0], dims[0], 1, 1)
-    shapes["decoder.middle.1.proj.bias"] = (dims[0],)
-    res("decoder.middle.2", dims[0], dims[0])
-    n = 0
-    cin = dims[0]
-    plan = [(dims[0], dims[1], "up3d"), (dims[1] // 2, dims[2], "up3d"), (dims[2] // 2, dims[3], "up2d"),
-            (dims[3] // 2, dims[4], None)]
-    for ci, co, up in plan:
-        cin = ci
-        for _ in range(3):
-            res(f"decoder.upsamples.{n}", cin, co)
-            cin = co
-            n += 1
-        if up is not None:
-            pre = f"decoder.upsamples.{n}"
-            shapes[pre + ".resample.1.weight"] = (co // 2, co, 3, 3)
-            shapes[pre + ".resample.1.bias"] = (co // 2,)
-            if up == "up3d":
-                conv3(pre + ".time_conv", co, 2 * co, (3, 1, 1))
-            n += 1
-    shapes["decoder.head.0.gamma"] = (dims[4], 1, 1, 1)
-    conv3("decoder.head.2", dims[4], 3, (3, 3, 3))
-    out = {}
-    for k, shp in shapes.items():
-        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(k.encode())) % (2 ** 31))
-        t = torch.randn(shp, generator=g)
-        if k.endswith("gamma"):
-            t = 1.0 + 0.1 * t
-        elif k.endswith("bias"):
-            t = 0.02 * t
-        else:
-            fan_in = 1
-            for d in shp[1:]:
-                fan_in *= d
-            t = t * (1.4 / fan_in ** 0.5)
-        out[k] = t
-    return out
+from realtime_video_b200.factory import synthetic_vae_params  # noqa: E402,F401  (seeded weights, shared)

@@ -30,6 +30,46 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# Optional per-kernel timing (bench.py roofline): CUDA events recorded on the launching stream
+# around every launch of a kernel family while enabled.
+_prof = None
+
+
+def profile_begin() -> None:
+    global _prof
+    _prof = {}
+
+
+def profile_end() -> dict:
+    """{family: {"flops": algorithmic FLOPs, "ms": summed launch durations, "n": launches}}.
+    Call after a synchronize."""
+    global _prof
+    rec, _prof = _prof or {}, None
+    out = {}
+    for fam, items in rec.items():
+        ms = sum(a.elapsed_time(b) for a, b, _ in items)
+        out[fam] = {"flops": float(sum(f for _, _, f in items)), "ms": ms, "n": len(items)}
+    return out
+
+
+class _Timed:
+    def __init__(self, family: str, flops: float):
+        self.family, self.flops = family, flops
+
+    def __enter__(self):
+        if _prof is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _prof is not None:
+            self.b.record()
+            _prof.setdefault(self.family, []).append((self.a, self.b, self.flops))
+        return False
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -84,9 +124,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         _req(gate, "gate", a.dtype)
         gs = gate.stride(0) if gate.dim() >= 2 else 0
     lib = _lib.load()
-    rc = lib.kr_gemm(_DT[a.dtype], epilogue, a.data_ptr(), lda, w.data_ptr(), w.stride(0),
-                     _ptr(bias), out.data_ptr(), ldc, M, N, K, _ptr(residual), ldr, _ptr(gate), gs,
-                     rows_per_gate, alpha, _stream())
+    with _Timed("gemm", 2.0 * M * N * K):
+        rc = lib.kr_gemm(_DT[a.dtype], epilogue, a.data_ptr(), lda, w.data_ptr(), w.stride(0),
+                         _ptr(bias), out.data_ptr(), ldc, M, N, K, _ptr(residual), ldr, _ptr(gate), gs,
+                         rows_per_gate, alpha, _stream())
     _lib.check(rc, "kr_gemm")
     _count()
     return out
@@ -111,9 +152,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, heads: int,
     if softmax_scale is None:
         softmax_scale = 1.0 / math.sqrt(128)
     lib = _lib.load()
-    rc = lib.kr_attn_fwd(_DT[q.dtype], q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv,
-                         out.data_ptr(), ldo, Lq, Lkv, heads, softmax_scale,
-                         1 if block_len > 0 else 0, block_len, window, pad_keys, _stream())
+    with _Timed("attention", 4.0 * Lq * Lkv * heads * 128):
+        rc = lib.kr_attn_fwd(_DT[q.dtype], q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv,
+                             out.data_ptr(), ldo, Lq, Lkv, heads, softmax_scale,
+                             1 if block_len > 0 else 0, block_len, window, pad_keys, _stream())
     _lib.check(rc, "kr_attn_fwd")
     _count()
     return out
@@ -277,7 +319,9 @@ def vae_conv(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]
     npr, npix, nfr = strides(out_norm)
     sp, spix, sfr = strides(residual)
     lib = _lib.load()
-    rc = lib.kr_vae_conv3d(_DT[x.dtype], cin, n, x.data_ptr(), t_in, weight.data_ptr(), weight.shape[0],
+    _fl = 2.0 * T * H * W * n * cin * kt * kh * kw
+    with _Timed("vae_conv", _fl):
+      rc = lib.kr_vae_conv3d(_DT[x.dtype], cin, n, x.data_ptr(), t_in, weight.data_ptr(), weight.shape[0],
                            _ptr(bias), cout, T, H, W, tw, th, kt, kh, kw, rp, rpix, rfr, npr, npix, nfr,
                            _ptr(gamma), sp, spix, sfr, _ptr(out_pix), _stream())
     _lib.check(rc, "kr_vae_conv3d")

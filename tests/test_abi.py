@@ -1,0 +1,62 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/krea_b200.h
+declares (no compute calls here)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from realtime_video_b200 import _lib
+    _lib.build()
+    return _lib.load()
+
+
+def header_symbols():
+    text = (ROOT / "include" / "krea_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = header_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in krea_b200.h but not exported"
+
+
+def test_bindings_cover_the_header(lib):
+    from realtime_video_b200 import _lib
+    declared = set(header_symbols()) - {"kr_version", "kr_last_error"}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_version_and_error_string(lib):
+    assert lib.kr_version() >= 100
+    assert isinstance(lib.kr_last_error(), (bytes, type(None)))
+
+
+def test_argument_validation_needs_no_gpu(lib):
+    """Bad arguments are rejected before any CUDA call: codes are negative, message is set."""
+    rc = lib.kr_gemm(0, 0, None, 0, None, 0, None, None, 0, 1, 1, 1, None, 0, None, 0, 0, ctypes.c_float(1.0), None)
+    assert rc == -1 and b"null" in lib.kr_last_error()
+    rc = lib.kr_attn_fwd(5, None, 0, None, 0, None, 0, None, 0, 1, 1, 1, ctypes.c_float(1.0), 0, 0, 0, 0, None)
+    assert rc == -1
+
+
+def test_product_path_has_no_cpu_fallback():
+    import torch
+    from realtime_video_b200 import _lib, ops
+    with pytest.raises(_lib.KreaB200Error):
+        ops.gemm(torch.zeros(4, 64, dtype=torch.bfloat16), torch.zeros(32, 64, dtype=torch.bfloat16))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = ROOT / "realtime_video_b200"
+    for f in pkg.rglob("*.py"):
+        src = f.read_text()
+        assert "from oracle" not in src and "import oracle" not in src, f"{f} imports the oracle"
