@@ -160,8 +160,11 @@ class DecoderEngine:
 
     MAX_CHUNK = 3          # latent frames per launch sequence
 
-    def __init__(self, decoder: VAEDecoder3d, conv2: nn.Module, mean: torch.Tensor, std: torch.Tensor):
+    def __init__(self, decoder: VAEDecoder3d, conv2: nn.Module, mean: torch.Tensor, std: torch.Tensor,
+                 single_mode: bool = False):
         self.decoder, self.conv2, self.mean, self.std = decoder, conv2, mean, std
+        # single_mode: semantics of demo_utils/vae.py (VAEDecoderWrapperSingle), see decode_single
+        self.single_mode = single_mode
         self._key = None
         self.H = self.W = None
 
@@ -345,7 +348,13 @@ class DecoderEngine:
             else:  # Resample
                 C = b["C"]
                 if b["mode"] == "upsample3d":
-                    if first:
+                    if first and self.single_mode:
+                        # demo_utils/vae.py:112-123: [zeros, x] on the channel axis -> after the
+                        # channel->time interleave a ZERO frame precedes every frame; cache untouched
+                        y = torch.zeros(2 * T, h, w, C, dtype=self.dtype, device=self.device)
+                        y[1::2] = x
+                        x, T = y, 2 * T
+                    elif first:
                         b["tcache"].zero_()                    # sentinel, time_conv skipped
                     else:
                         tc = b["tconv"]
@@ -363,6 +372,9 @@ class DecoderEngine:
                                 xs = x[s0:s0 + step]
                                 if step >= 2:
                                     b["tcache"].copy_(xs[-2:])
+                                elif self.single_mode:         # demo_utils/vae.py:106-111: [0, x]
+                                    b["tcache"][0].zero_()
+                                    b["tcache"][1].copy_(xs[0])
                                 else:
                                     old_last = b["tcache"][1]
                                     pad = torch.where(old_last == 0, torch.zeros_like(xs[0]), xs[0])
@@ -411,6 +423,27 @@ class DecoderEngine:
         return pix[None], self.export_cache()
 
 
+    def decode_single(self, z: torch.Tensor, is_first_frame, feat_cache: List[Optional[torch.Tensor]]):
+        """demo_utils/vae.py:167-195: one latent frame, explicit first-frame flag, 32 positional
+        caches -> (pixels [1, 4, 3, H, W] in z.dtype clamped to [-1, 1], list of 32 caches)."""
+        assert z.shape[0] == 1 and z.shape[1] == 1
+        zt = z[0]
+        dtype = zt.dtype if zt.dtype in (torch.float16, torch.bfloat16) else torch.float16
+        self._prepare(dtype, zt.device, zt.shape[-2], zt.shape[-1])
+        mine = [c for c in self.export_cache() if c is not None]
+        if len(feat_cache) != len(mine):
+            raise ValueError(f"expected {len(mine)} cache tensors, got {len(feat_cache)}")
+        for src, dst in zip(feat_cache, mine):
+            if src.data_ptr() != dst.data_ptr():
+                # reference cache layout is [1, C, 2, H, W]; ours [2, H, W, C]
+                if src.dim() == 5:
+                    src = src[0].permute(1, 2, 3, 0)
+                dst[..., :src.shape[-1]].copy_(src)
+        first = bool(is_first_frame.item()) if torch.is_tensor(is_first_frame) else bool(is_first_frame)
+        pix = self.decode_chunk(zt.to(dtype), first=first)
+        return pix[None].to(z.dtype), [c for c in self.export_cache() if c is not None]
+
+
 # ---------------------------------------------------------------------------------------------
 # the reference-facing wrappers
 # ---------------------------------------------------------------------------------------------
@@ -442,6 +475,31 @@ class VAEDecoderWrapper(nn.Module):
         eng = self.engine
         eng.mean, eng.std = self.mean, self.std
         return eng.decode(z, list(feat_cache))
+
+
+class VAEDecoderWrapperSingle(nn.Module):
+    """demo_utils/vae.py:150-195: ``forward(z[1,1,16,h,w], is_first_frame, *32 caches) ->
+    (pixels [1,4,3,H,W] (z.dtype), 32 caches)``.  NOT interchangeable with VAEDecoderWrapper: the
+    first latent frame also yields 4 frames (a zero frame is interleaved in front of it) and
+    one-frame time_conv chunks cache [0, x]."""
+
+    def __init__(self):
+        super().__init__()
+        self.decoder = VAEDecoder3d()
+        self.mean = torch.tensor(MEAN, dtype=torch.float32)
+        self.std = torch.tensor(STD, dtype=torch.float32)
+        self.z_dim = 16
+        self.conv2 = CausalConv3d(self.z_dim, self.z_dim, 1)
+        self._engine: Optional[DecoderEngine] = None
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def forward(self, z: torch.Tensor, is_first_frame: torch.Tensor, *feat_cache):
+        if self._engine is None:
+            self._engine = DecoderEngine(self.decoder, self.conv2, self.mean, self.std, single_mode=True)
+        return self._engine.decode_single(z, is_first_frame, list(feat_cache))
 
 
 class WanVAEDecoderCore:

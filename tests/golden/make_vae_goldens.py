@@ -43,9 +43,29 @@ def run(tag, h, w, sub):
         print(tag, call, tuple(px.shape), float(px.abs().mean()), flush=True)
 
 
+@torch.no_grad()
+def run_single(tag, h, w):
+    """demo_utils.vae.VAEDecoderWrapperSingle: 3 latent frames one at a time (first flag on #0)."""
+    ns = ref_shim.install()
+    m = ns.vae_single.VAEDecoderWrapperSingle()
+    m.load_state_dict(synthetic_vae_params(seed=0), strict=False)
+    m = m.float().eval()
+    shapes = [(16, h, w)] + [(384, h, w)] * 11 + [(192, 2 * h, 2 * w)] + [(384, 2 * h, 2 * w)] * 6 \
+        + [(192, 4 * h, 4 * w)] * 6 + [(96, 8 * h, 8 * w)] * 7          # demo_utils/constant.py:6-39
+    cache = [torch.zeros(1, c, 2, hh, ww) for (c, hh, ww) in shapes]
+    g = torch.Generator().manual_seed(5)
+    for i in range(3):
+        z = torch.randn(1, 1, 16, h, w, generator=g)
+        OUT[f"{tag}/z{i}"] = z.numpy()
+        px, cache = m(z, torch.tensor(i == 0), *cache)
+        OUT[f"{tag}/px{i}"] = px.contiguous().numpy()
+        print(tag, i, tuple(px.shape), float(px.abs().mean()), flush=True)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     run("s8x12", 8, 12, 1)
     run("s16x24", 16, 24, 2)
+    run_single("single8x12", 8, 12)
     np.savez_compressed(HERE / "vae_small.npz", **OUT)
     print("vae_small.npz", sum(v.nbytes for v in OUT.values()) / 1e6, "MB raw")

@@ -76,3 +76,24 @@ def test_conv_kernel_vs_torch_conv3d():
                      tile=_tile_for(H, W), out_raw=out)
         r = rel_l2(out, ref)
         assert r < 2e-3, f"conv {cin}->{cout} taps {taps}: rel_l2={r:.3e}"
+
+
+def test_single_frame_wrapper_vs_reference_golden():
+    """demo_utils.vae.VAEDecoderWrapperSingle semantics (4 frames even for the first latent)."""
+    from realtime_video_b200.vae import VAEDecoderWrapperSingle
+    g = load_npz("vae_small.npz")
+    m = VAEDecoderWrapperSingle()
+    m.load_state_dict(synthetic_vae_params(seed=0), strict=False)
+    m = m.to(device="cuda", dtype=torch.float16).eval()
+    h, w = 8, 12
+    shapes = [(16, h, w)] + [(384, h, w)] * 11 + [(192, 2 * h, 2 * w)] + [(384, 2 * h, 2 * w)] * 6 \
+        + [(192, 4 * h, 4 * w)] * 6 + [(96, 8 * h, 8 * w)] * 7
+    cache = [torch.zeros(1, c, 2, hh, ww, device="cuda", dtype=torch.float16) for (c, hh, ww) in shapes]
+    with torch.no_grad():
+        for i in range(3):
+            z = g[f"single8x12/z{i}"].cuda().half()
+            px, cache = m(z, torch.tensor(i == 0, device="cuda"), *cache)
+            assert px.shape == (1, 4, 3, 64, 96) and px.dtype == torch.float16 and len(cache) == 32
+            ref = g[f"single8x12/px{i}"]
+            r = rel_l2(px.float().cpu(), ref)
+            assert r < 2e-2, f"single frame {i}: rel_l2={r:.3e}"
