@@ -219,18 +219,44 @@ def run_reference_arm(args, rank, world):
                        "frames/s of a whole 12-frame block"},
             "cpu_baseline": ref.describe(t_layer, len(ts)),
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line: park the real stdout and point fd 1 at stderr, so
+    anything a library prints (e.g. NCCL's version banner) cannot land in front of it."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--parallel", default="replicas", choices=["replicas", "sp"],
+                    help="N>1: independent replicas (default; the path does not shard) or ONE stream "
+                         "sequence-parallel over all GPUs (realtime_video_b200/parallel.py)")
     ap.add_argument("--layers", type=int, default=LAYERS, help=argparse.SUPPRESS)      # debugging only
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
@@ -248,6 +274,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
+        # stdout carries exactly ONE JSON line: keep NCCL's "NCCL version ..." banner off it
+        # (the image exports NCCL_DEBUG; NCCL writes its banner/diagnostics to stdout unless redirected)
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(tempfile.gettempdir(), "nccl_bench.%h.%p.log"))
         dist.init_process_group("nccl", device_id=dev)
 
     from realtime_video_b200 import factory, ops
@@ -273,8 +302,14 @@ def main():
         return float(t.item())
 
     # ---------------- device-resident run (value) ----------------
-    params = GenerateParams(num_blocks=W + K, seed=42 + rank)
-    sess = GenerationSession(params, models, prompt_embeds=pe, device=dev)
+    sp_mode = world > 1 and args.parallel == "sp"
+    streams = 1 if sp_mode else world           # independent video streams in flight
+    if sp_mode:
+        from realtime_video_b200.parallel import SequenceParallel
+        transformer.model.sp = SequenceParallel()
+    decode = (not sp_mode) or rank == 0         # one stream -> one VAE decode (rank 0)
+    params = GenerateParams(num_blocks=W + K, seed=42 + (0 if sp_mode else rank))
+    sess = GenerationSession(params, models, prompt_embeds=pe, device=dev, decode=decode)
     with torch.inference_mode():
         for _ in range(W):
             sess.generate_block()
@@ -294,12 +329,14 @@ def main():
         prof = ops.profile_end()
         clk = clocks.stop() if rank == 0 else None
     ms = max_over_ranks(e0.elapsed_time(e1))
-    assert px.shape == (1, 12, 3, 480, 832) and px.dtype == torch.float32
-    value = world * K * FRAMES_PER_STEP / (ms / 1e3)
+    if decode:
+        assert px.shape == (1, 12, 3, 480, 832) and px.dtype == torch.float32
+    value = streams * K * FRAMES_PER_STEP / (ms / 1e3)
 
     # ---------------- end-to-end run (host buffers) ----------------
     nf = 3
-    sess2 = GenerationSession(GenerateParams(num_blocks=W + K, seed=1042 + rank), models, prompt_embeds=pe, device=dev)
+    sess2 = GenerationSession(GenerateParams(num_blocks=W + K, seed=1042 + (0 if sp_mode else rank)), models,
+                              prompt_embeds=pe, device=dev, decode=decode)
     host_noise = sess2.noise.cpu().pin_memory()
     host_px = torch.empty(1, 12, 3, 480, 832, dtype=torch.float32).pin_memory()
     with torch.inference_mode():
@@ -312,12 +349,13 @@ def main():
             s = sess2.current_start_frame
             sess2.noise[:, s:s + nf].copy_(host_noise[:, s:s + nf], non_blocking=True)      # H2D
             px = sess2.generate_block()
-            host_px.copy_(px, non_blocking=True)                                            # D2H
+            if decode:
+                host_px.copy_(px, non_blocking=True)                                        # D2H
             torch.cuda.current_stream().synchronize()                                       # frames usable on host
         t1.record()
         barrier()
     ms_e2e = max_over_ranks(t0.elapsed_time(t1))
-    e2e = world * K * FRAMES_PER_STEP / (ms_e2e / 1e3)
+    e2e = streams * K * FRAMES_PER_STEP / (ms_e2e / 1e3)
     h2d = host_noise[:, :nf].numel() * host_noise.element_size()
     d2h = host_px.numel() * host_px.element_size()
 
@@ -356,13 +394,15 @@ def main():
     line = {
         "metric": "frames_per_second_832x480_4step_t2v", "value": value, "unit": "frames/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": (value / 11.0) if world == 1 else None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "strong" if sp_mode else "weak", "vs_baseline": (value / 11.0) if world == 1 else None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "model_dims": "Wan2.1-T2V-14B (40 layers, d 5120, ffn 13824, 40 heads)"
                    if args.layers == LAYERS else f"DEBUG {args.layers} layers",
                    "resolution": "832x480", "denoise_steps": 4, "kv_cache_num_frames": 3, "frames_per_step": 12,
                    "passes_per_step": "1 KV recompute + 4 denoise DiT passes + VAE decode (fp16)",
                    "first_frame": "kept (reference keep_first_frame=True; VAE-encoder re-encode is a 'next' row)",
-                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (path does not shard)",
+                   "parallelism": "1 GPU" if world == 1 else (
+                       f"ONE stream, Ulysses sequence parallel over {world} GPUs (rows<->heads all-to-all, NCCL); "
+                       f"VAE decode on rank 0" if sp_mode else f"{world} independent replicas (path does not shard)"),
                    "l2": "weights (28 GB/pass) and KV cache exceed the 126 MB L2 every step; no flush needed",
                    "dit_tflop_per_step": block_tflop},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -373,7 +413,7 @@ def main():
         "cpu_baseline": cpu,
         "baseline_note": "vs_baseline = value / 11 fps (reference README.md:31: 11 fps on 1x B200, 4 steps); null for N>1 (nothing published)",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 if __name__ == "__main__":

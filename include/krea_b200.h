@@ -50,11 +50,15 @@ const char* kr_last_error(void);
  *   ffn.0 + GELU(tanh), ffn.2   wan/modules/causal_model.py:433-435
  *   cross-attn q/k/v/o          wan/modules/model.py:183-190, :226-227
  *   patch/text/time embeddings, time_projection, head   causal_model.py:874-902, :507-522
- * Needs K % 8 == 0, N % 32 == 0, ld* % 8 == 0.  bias/residual/gate may be NULL when unused. */
+ * Needs K % 8 == 0, N % 32 == 0, ld* % 8 == 0.  bias/residual/gate may be NULL when unused.
+ * out2 (optional): output columns >= n_split (a multiple of 256) are written to out2 instead,
+ * starting at its column 0 with leading dimension ldc2 — the V third of to_qkv goes straight
+ * into the KV-cache slot (causal_model.py:385).  row_offset: global index of local row 0 when the
+ * token rows are sharded across GPUs (gate row = (row + row_offset) / rows_per_gate). */
 int kr_gemm(int dtype, int epilogue, const void* a, int lda, const void* w, int ldw,
             const void* bias, void* out, int ldc, int M, int N, int K, const void* residual,
             int ldr, const void* gate, int gate_stride, int rows_per_gate, float alpha,
-            void* stream);
+            void* out2, int ldc2, int n_split, int row_offset, void* stream);
 
 /* softmax(scale * q k^T) v, head_dim 128, [L, heads, 128] layout, bf16/fp16, fp32 softmax.
  * mask_mode 0: none (cached self-attention causal_model.py:386-390, cross-attention
@@ -72,7 +76,7 @@ int kr_attn_fwd(int dtype, const void* q, int ldq, const void* k, int ldk, const
  * Replaces wan/modules/model.py:88-98 + causal_model.py:466-471, :482-485, :520-522 (bf16). */
 int kr_ln_modulate(const void* x, int ldx, void* out, int ldo, int rows, int D, float eps,
                    const void* w, const void* b, const void* mod, int mod_rows, int shift_idx,
-                   int scale_idx, int rows_per_frame, void* stream);
+                   int scale_idx, int rows_per_frame, int row_offset, void* stream);
 
 /* q,k: WanRMSNorm over D (model.py:69-85) then 3-axis RoPE (causal_model.py:143-171) written to
  * q_out and to the K cache slot; v copied to the V cache slot (causal_model.py:378-385, :310-311).
@@ -80,7 +84,7 @@ int kr_ln_modulate(const void* x, int ldx, void* out, int ldo, int rows, int D, 
 int kr_qkv_norm_rope(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
                      const void* wq, const void* wk, void* q_out, int ldqo, void* k_out, int ldko,
                      void* v_out, int ldvo, const void* rope, int rows, int D, int head_dim,
-                     int grid_h, int grid_w, int start_frame, float eps, void* stream);
+                     int grid_h, int grid_w, int start_frame, int row_offset, float eps, void* stream);
 
 /* WanRMSNorm rows (cross-attention q / k): model.py:69-85, :183-190 */
 int kr_rmsnorm(const void* x, int ldx, void* out, int ldo, const void* w, int rows, int D,

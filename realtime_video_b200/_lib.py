@@ -91,11 +91,12 @@ _sz = ctypes.c_size_t
 
 # name -> argtypes; every function returns int except where noted
 SIGNATURES = {
-    "kr_gemm": [_i, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _f, _vp],
+    "kr_gemm": [_i, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _f, _vp, _i, _i,
+                _i, _vp],
     "kr_attn_fwd": [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _f, _i, _i, _i, _i, _vp],
-    "kr_ln_modulate": [_vp, _i, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "kr_ln_modulate": [_vp, _i, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "kr_qkv_norm_rope": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i,
-                         _i, _i, _i, _i, _i, _f, _vp],
+                         _i, _i, _i, _i, _i, _i, _f, _vp],
     "kr_rmsnorm": [_vp, _i, _vp, _i, _vp, _i, _i, _f, _vp],
     "kr_add_modulation": [_vp, _vp, _i, _vp, _i, _i, _i, _vp],
     "kr_activation": [_vp, _vp, _sz, _i, _vp],

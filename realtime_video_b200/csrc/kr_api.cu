@@ -22,13 +22,14 @@ const char* kr_last_error(void) { return kr::last_error(); }
 int kr_gemm(int dtype, int epilogue, const void* a, int lda, const void* w, int ldw,
             const void* bias, void* out, int ldc, int M, int N, int K, const void* residual,
             int ldr, const void* gate, int gate_stride, int rows_per_gate, float alpha,
-            void* stream) {
+            void* out2, int ldc2, int n_split, int row_offset, void* stream) {
   KR_REQUIRE(a && w && out, "null a/w/out");
   KR_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (bf16) or 1 (fp16)");
   kr::GemmParams p;
   p.out = out; p.bias = bias; p.residual = residual; p.gate = gate;
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.ldr = ldr; p.gate_stride = gate_stride;
   p.rows_per_gate = rows_per_gate; p.alpha = alpha;
+  p.out2 = out2; p.ldc2 = ldc2; p.n_split = n_split; p.row_offset = row_offset;
   return kr::gemm_tn(dtype, epilogue, a, lda, w, ldw, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -47,16 +48,16 @@ int kr_attn_fwd(int dtype, const void* q, int ldq, const void* k, int ldk, const
 
 int kr_ln_modulate(const void* x, int ldx, void* out, int ldo, int rows, int D, float eps,
                    const void* w, const void* b, const void* mod, int mod_rows, int shift_idx,
-                   int scale_idx, int rows_per_frame, void* stream) {
+                   int scale_idx, int rows_per_frame, int row_offset, void* stream) {
   KR_REQUIRE(x && out, "null x/out");
   return kr::ln_modulate(x, ldx, out, ldo, rows, D, eps, w, b, mod, mod_rows, shift_idx, scale_idx,
-                         rows_per_frame, static_cast<cudaStream_t>(stream));
+                         rows_per_frame, row_offset, static_cast<cudaStream_t>(stream));
 }
 
 int kr_qkv_norm_rope(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
                      const void* wq, const void* wk, void* q_out, int ldqo, void* k_out, int ldko,
                      void* v_out, int ldvo, const void* rope, int rows, int D, int head_dim,
-                     int grid_h, int grid_w, int start_frame, float eps, void* stream) {
+                     int grid_h, int grid_w, int start_frame, int row_offset, float eps, void* stream) {
   KR_REQUIRE(q && k && wq && wk && q_out && k_out, "null q/k/weights/outputs");
   KR_REQUIRE((v == nullptr) == (v_out == nullptr), "v and v_out must both be given or both null");
   kr::QkvPostParams p;
@@ -69,6 +70,7 @@ int kr_qkv_norm_rope(const void* q, int ldq, const void* k, int ldk, const void*
   p.v_out = static_cast<uint16_t*>(v_out); p.ldvo = ldvo;
   p.rope = static_cast<const float2*>(rope);
   p.D = D; p.head_dim = head_dim; p.grid_h = grid_h; p.grid_w = grid_w; p.start_frame = start_frame;
+  p.row_offset = row_offset;
   p.eps = eps;
   return kr::qkv_post(p, rows, static_cast<cudaStream_t>(stream));
 }

@@ -23,6 +23,7 @@
 #include "kr_ops.h"
 
 #include <cmath>
+#include <cstdlib>
 
 namespace kr {
 
@@ -36,7 +37,7 @@ static constexpr int kHalfBytes = kTileBytes / 2;           // one 64-column swi
 static constexpr int kAttnThreads = 384;
 static constexpr int kAttnSmem = 2 * kTileBytes + kKvStages * kTileBytes + 1024 + 256;
 
-template <bool kBf16>
+template <bool kBf16, bool kPHalf>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -56,8 +57,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int q0 = blockIdx.x * 2 * kTileQ;
+  // linear CTA order: every two-tile CTA of every head first, the single-tile ones (if the last
+  // 256-row block of a head holds <= 128 rows) last, so they fill the tail of the final wave
+  const int nqb = (p.Lq + 2 * kTileQ - 1) / (2 * kTileQ);
+  const bool has_short = (p.Lq - (nqb - 1) * 2 * kTileQ) <= kTileQ;
+  const int full_per_head = has_short ? nqb - 1 : nqb;
+  int head, qb;
+  if (static_cast<int>(blockIdx.x) < p.heads * full_per_head) {
+    head = blockIdx.x / full_per_head;
+    qb = blockIdx.x % full_per_head;
+  } else {
+    head = blockIdx.x - p.heads * full_per_head;
+    qb = nqb - 1;
+  }
+  const int q0 = qb * 2 * kTileQ;
 
   // number of KV tiles this CTA visits
   int kv_limit = p.Lkv;
@@ -68,6 +81,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     if (hi < kv_limit) kv_limit = hi;
   }
   const int n_tiles = (kv_limit + kTileKV - 1) / kTileKV;
+  // second 128-row query tile entirely past Lq (last CTA of a head): its MMAs / softmax are skipped
+  const bool two = (q0 + kTileQ) < p.Lq;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_q);
@@ -125,99 +140,134 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_qk = make_idesc<kBf16>(128, 128, 0, 0);   // A,B K-major
-    constexpr uint32_t idesc_pv = make_idesc<kBf16>(128, 128, 0, 1);   // B (=V) MN-major
+    // P.V: A = P from TMEM (fp16 when kPHalf, else the KV dtype), B = V MN-major in the KV dtype
+    constexpr uint32_t idesc_pv = make_idesc_ab(128, 128, (kPHalf || !kBf16) ? 0u : 1u, kBf16 ? 1u : 0u, 0, 1);
     const uint32_t q_addr = smem_u32(smem_q);
     const uint32_t kv_addr = smem_u32(smem_kv);
     const uint32_t tS[2] = {tmem_base + 0, tmem_base + 128};
     const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
 
-    auto issue_qk = [&](int wg, int stage) {
-      const uint32_t a = q_addr + wg * kTileBytes;
+    // S buffer `sb` = Q tile `qt` . K(stage)^T
+    auto issue_qk = [&](int qt, int sb, int stage) {
+      const uint32_t a = q_addr + qt * kTileBytes;
       const uint32_t b = kv_addr + stage * kTileBytes;
 #pragma unroll
       for (int k = 0; k < kHeadDim / 16; ++k) {
         const uint32_t off = (k >> 2) * kHalfBytes + (k & 3) * 32;
-        umma_ss(tS[wg], make_smem_desc(a + off, 16, 1024), make_smem_desc(b + off, 16, 1024),
+        umma_ss(tS[sb], make_smem_desc(a + off, 16, 1024), make_smem_desc(b + off, 16, 1024),
                 idesc_qk, k != 0 ? 1u : 0u);
       }
     };
-    auto issue_pv = [&](int wg, int stage, bool first) {
+    // O buffer `ob` += P (16-bit, aliasing S buffer `sb`) . V(stage)
+    auto issue_pv = [&](int ob, int sb, int stage, bool first) {
       const uint32_t b = kv_addr + stage * kTileBytes;
 #pragma unroll
       for (int k = 0; k < kTileKV / 16; ++k) {
         // P: 16 keys = 8 TMEM columns per k-step; V: 16 key rows of 128 B per panel
-        umma_ts(tO[wg], tS[wg] + k * 8, make_smem_desc(b + k * 2048, kHalfBytes, 1024), idesc_pv,
+        umma_ts(tO[ob], tS[sb] + k * 8, make_smem_desc(b + k * 2048, kHalfBytes, 1024), idesc_pv,
                 (first && k == 0) ? 0u : 1u);
       }
     };
-
-    int stage = 0;
-    uint32_t phase = 0;
-    auto advance = [&]() {
-      if (++stage == kKvStages) {
-        stage = 0;
-        phase ^= 1;
-      }
-    };
+    // ring items: K_j = 2j, V_j = 2j + 1
+    auto st = [](int item) { return item % kKvStages; };
+    auto ph = [](int item) { return static_cast<uint32_t>((item / kKvStages) & 1); };
 
     mbar_wait(q_full, 0);
-    // prologue: S0 = Q0 K0^T, S1 = Q1 K0^T
-    mbar_wait(&kv_full[stage], phase);
-    tc_fence_after();
-    if (lane == 0) {
-      issue_qk(0, stage);
-      umma_commit(&s_full[0]);
-      issue_qk(1, stage);
-      umma_commit(&s_full[1]);
-      umma_commit(&kv_empty[stage]);
-    }
-    __syncwarp();
-    advance();
-    for (int j = 0; j < n_tiles; ++j) {
-      const int v_stage = stage;
-      mbar_wait(&kv_full[v_stage], phase);   // V_j
-      advance();
-      const int k_stage = stage;
-      const bool more = (j + 1 < n_tiles);
-      // ---- warpgroup 0 ----
-      mbar_wait(&p_ready[0], j & 1);
+    if (two) {
+      // ---- two query tiles: ping-pong between the softmax warpgroups ----
+      mbar_wait(&kv_full[st(0)], ph(0));
       tc_fence_after();
-      if (lane == 0) issue_pv(0, v_stage, j == 0);
+      if (lane == 0) {
+        issue_qk(0, 0, st(0));
+        umma_commit(&s_full[0]);
+        issue_qk(1, 1, st(0));
+        umma_commit(&s_full[1]);
+        umma_commit(&kv_empty[st(0)]);
+      }
       __syncwarp();
-      if (more) {
-        mbar_wait(&kv_full[k_stage], phase);   // K_{j+1}
+      for (int j = 0; j < n_tiles; ++j) {
+        const int vi = 2 * j + 1, ki = 2 * j + 2;
+        const bool more = (j + 1 < n_tiles);
+        mbar_wait(&kv_full[st(vi)], ph(vi));   // V_j
+        mbar_wait(&p_ready[0], j & 1);
+        tc_fence_after();
+        if (lane == 0) issue_pv(0, 0, st(vi), j == 0);
+        __syncwarp();
+        if (more) {
+          mbar_wait(&kv_full[st(ki)], ph(ki));   // K_{j+1}
+          tc_fence_after();
+          if (lane == 0) {
+            issue_qk(0, 0, st(ki));
+            umma_commit(&s_full[0]);
+          }
+          __syncwarp();
+        }
+        mbar_wait(&p_ready[1], j & 1);
         tc_fence_after();
         if (lane == 0) {
-          issue_qk(0, k_stage);
-          umma_commit(&s_full[0]);
+          issue_pv(1, 1, st(vi), j == 0);
+          umma_commit(&kv_empty[st(vi)]);
+          if (more) {
+            issue_qk(1, 1, st(ki));
+            umma_commit(&s_full[1]);
+            umma_commit(&kv_empty[st(ki)]);
+          }
         }
         __syncwarp();
       }
-      // ---- warpgroup 1 ----
-      mbar_wait(&p_ready[1], j & 1);
+    } else {
+      // ---- one query tile (last CTA of a head): S double-buffered so Q.K_{j+1}^T overlaps softmax(j) ----
+      mbar_wait(&kv_full[st(0)], ph(0));
       tc_fence_after();
       if (lane == 0) {
-        issue_pv(1, v_stage, j == 0);
-        umma_commit(&kv_empty[v_stage]);
-        if (more) {
-          issue_qk(1, k_stage);
-          umma_commit(&s_full[1]);
-          umma_commit(&kv_empty[k_stage]);
-        }
+        issue_qk(0, 0, st(0));
+        umma_commit(&s_full[0]);
+        umma_commit(&kv_empty[st(0)]);
       }
       __syncwarp();
-      if (more) advance();
+      if (n_tiles > 1) {
+        mbar_wait(&kv_full[st(2)], ph(2));
+        tc_fence_after();
+        if (lane == 0) {
+          issue_qk(0, 1, st(2));
+          umma_commit(&s_full[1]);
+          umma_commit(&kv_empty[st(2)]);
+        }
+        __syncwarp();
+      }
+      for (int j = 0; j < n_tiles; ++j) {
+        const int vi = 2 * j + 1, ki = 2 * (j + 2);
+        const int sb = j & 1;
+        mbar_wait(&kv_full[st(vi)], ph(vi));   // V_j
+        mbar_wait(&p_ready[sb], (j >> 1) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          issue_pv(0, sb, st(vi), j == 0);
+          umma_commit(&kv_empty[st(vi)]);
+        }
+        __syncwarp();
+        if (j + 2 < n_tiles) {
+          mbar_wait(&kv_full[st(ki)], ph(ki));   // K_{j+2}
+          tc_fence_after();
+          if (lane == 0) {
+            issue_qk(0, sb, st(ki));
+            umma_commit(&s_full[sb]);
+            umma_commit(&kv_empty[st(ki)]);
+          }
+          __syncwarp();
+        }
+      }
     }
     if (lane == 0) umma_commit(o_final);
     __syncwarp();
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && (two || warp < 8)) {
     // ===================== softmax warpgroups =====================
     const int wg = (warp - 4) >> 2;
     const int quarter = warp & 3;
     const int row_in_tile = quarter * 32 + lane;
     const int q_row = q0 + wg * kTileQ + row_in_tile;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t tS = tmem_base + lane_off + wg * 128;
+    const uint32_t tS_base = tmem_base + lane_off;
     const uint32_t tO = tmem_base + lane_off + 256 + wg * 128;
 
     int row_hi = p.Lkv, row_lo = 0;
@@ -235,7 +285,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const float sl2 = p.scale_log2;
 
     for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(&s_full[wg], j & 1);
+      // two tiles: S buffer = warpgroup, one completion per KV tile; one tile: buffers alternate
+      const int sb = two ? wg : (j & 1);
+      const uint32_t par = two ? static_cast<uint32_t>(j & 1) : static_cast<uint32_t>((j >> 1) & 1);
+      const uint32_t tS = tS_base + sb * 128;
+      mbar_wait(&s_full[sb], par);
       tc_fence_after();
       uint32_t r0[32], r1[32], r2[32], r3[32];
       tmem_ld_x32(tS + 0, r0);
@@ -283,6 +337,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const float nms = (m_used == -INFINITY) ? 0.f : -m_used * sl2;
       float rowsum = 0.f;
       uint32_t pk[64];
+      if constexpr (kPHalf) {
+        // P in fp16: the exponent argument is formed in fp32 (a = s*c - m), rounded to f16x2 and
+        // exponentiated two-at-a-time on the MUFU (ex2.approx.ftz.f16x2): half the MUFU work and
+        // no pack instructions; |a| <= 16 where it matters, so the f16 argument error (<= 2^-8)
+        // is below the 2^-9 relative rounding of a bf16 P.  Row sums: short f16x2 trees -> fp32.
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          pk[c] = ex2_f16x2(fmaf(__uint_as_float(r0[2 * c]), sl2, nms), fmaf(__uint_as_float(r0[2 * c + 1]), sl2, nms));
+          pk[16 + c] = ex2_f16x2(fmaf(__uint_as_float(r1[2 * c]), sl2, nms), fmaf(__uint_as_float(r1[2 * c + 1]), sl2, nms));
+          pk[32 + c] = ex2_f16x2(fmaf(__uint_as_float(r2[2 * c]), sl2, nms), fmaf(__uint_as_float(r2[2 * c + 1]), sl2, nms));
+          pk[48 + c] = ex2_f16x2(fmaf(__uint_as_float(r3[2 * c]), sl2, nms), fmaf(__uint_as_float(r3[2 * c + 1]), sl2, nms));
+        }
+#pragma unroll
+        for (int c = 0; c < 64; c += 4) {
+          const __half2 s4 = __hadd2(__hadd2(*reinterpret_cast<__half2*>(&pk[c]), *reinterpret_cast<__half2*>(&pk[c + 1])),
+                                     __hadd2(*reinterpret_cast<__half2*>(&pk[c + 2]), *reinterpret_cast<__half2*>(&pk[c + 3])));
+          const float2 f = __half22float2(s4);
+          rowsum += f.x + f.y;
+        }
+      } else {
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         float a0 = fast_exp2(fmaf(__uint_as_float(r0[2 * c]), sl2, nms));
@@ -299,12 +373,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         pk[32 + c] = kBf16 ? pack_bf16x2(c0, c1) : pack_f16x2(c0, c1);
         pk[48 + c] = kBf16 ? pack_bf16x2(d0, d1) : pack_f16x2(d0, d1);
       }
+      }
       l_run += rowsum;
       tmem_st_x32(tS + 0, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
       tmem_st_x32(tS + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_ready[wg]);
+      mbar_arrive(&p_ready[sb]);
     }
 
     // ---- epilogue: O / l -> global ----
@@ -377,9 +452,13 @@ int attn_fwd(int dtype, const void* q, int ldq, const void* k, int ldk, const vo
   if (rc != KR_OK) return rc;
   rc = make_tmap_2d(&tv, v, p.Lkv, static_cast<uint64_t>(p.heads) * kHeadDim, ldv, kTileKV, 64, bf);
   if (rc != KR_OK) return rc;
-  auto kern = bf ? attn_fwd_kernel<true> : attn_fwd_kernel<false>;
+  // KR_ATTN_P_F16=1 selects the experimental fp16-P softmax (exp on f16x2) instead of the default
+  // bf16-P one (fp32 exp per element, P rounded to the KV dtype like FlashAttention-2)
+  static const bool p_f16 = [] { const char* e = getenv("KR_ATTN_P_F16"); return e != nullptr && e[0] == '1'; }();
+  auto kern = bf ? (p_f16 ? attn_fwd_kernel<true, true> : attn_fwd_kernel<true, false>)
+                 : attn_fwd_kernel<false, false>;
   static bool attr_set[2] = {false, false};
-  if (!attr_set[bf ? 0 : 1]) {
+  if (!attr_set[bf ? 0 : 1]) {   // (p_f16 is process-constant, so one flag per dtype suffices)
     cudaError_t e =
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e != cudaSuccess) {
@@ -388,7 +467,7 @@ int attn_fwd(int dtype, const void* q, int ldq, const void* k, int ldk, const vo
     }
     attr_set[bf ? 0 : 1] = true;
   }
-  dim3 grid((p.Lq + 2 * kTileQ - 1) / (2 * kTileQ), p.heads);
+  dim3 grid(((p.Lq + 2 * kTileQ - 1) / (2 * kTileQ)) * p.heads);
   kern<<<grid, kAttnThreads, kAttnSmem, stream>>>(tq, tk, tv, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -186,6 +186,13 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t M, uint32_t N, uint32
          (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// same with independent A / B element formats (0 = f16, 1 = bf16)
+__host__ __device__ constexpr uint32_t make_idesc_ab(uint32_t M, uint32_t N, uint32_t a_fmt, uint32_t b_fmt,
+                                                     uint32_t a_mn_major, uint32_t b_mn_major) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | (a_mn_major << 15) | (b_mn_major << 16) |
+         ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 // ---------------------------------------------------------------------------
 // tcgen05: mma / commit
 // ---------------------------------------------------------------------------
@@ -281,6 +288,13 @@ KR_DEVICE float2 unpack_bf16x2(uint32_t u) {
 KR_DEVICE float2 unpack_f16x2(uint32_t u) {
   __half2 v = *reinterpret_cast<__half2*>(&u);
   return __half22float2(v);
+}
+// 2^lo, 2^hi as packed f16x2 (lo in the low half): one cvt.pack + one MUFU op for two values
+KR_DEVICE uint32_t ex2_f16x2(float lo, float hi) {
+  uint32_t h, y;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(h));
+  return y;
 }
 KR_DEVICE float fast_exp2(float x) {
   float y;

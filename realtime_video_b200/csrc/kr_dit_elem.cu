@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kRowThreads)
 ln_modulate_kernel(const uint16_t* __restrict__ x, int ldx, uint16_t* __restrict__ out, int ldo,
                    int D, float eps, const uint16_t* __restrict__ w, const uint16_t* __restrict__ b,
                    const uint16_t* __restrict__ mod, int mod_rows, int shift_idx, int scale_idx,
-                   int rows_per_frame) {
+                   int rows_per_frame, int row_offset) {
   __shared__ float red[4];
   const int row = blockIdx.x;
   const uint16_t* xr = x + static_cast<size_t>(row) * ldx;
@@ -92,7 +92,7 @@ ln_modulate_kernel(const uint16_t* __restrict__ x, int ldx, uint16_t* __restrict
   }
   const float rstd = rsqrtf(block_sum(ss, red) / D + eps);
   const uint16_t* mrow = nullptr;
-  if (mod != nullptr) mrow = mod + static_cast<size_t>(row / rows_per_frame) * mod_rows * D;
+  if (mod != nullptr) mrow = mod + static_cast<size_t>((row + row_offset) / rows_per_frame) * mod_rows * D;
   uint16_t* orow = out + static_cast<size_t>(row) * ldo;
 #pragma unroll
   for (int i = 0; i < kMaxVec; ++i) {
@@ -124,7 +124,7 @@ ln_modulate_kernel(const uint16_t* __restrict__ x, int ldx, uint16_t* __restrict
 
 int ln_modulate(const void* x, int ldx, void* out, int ldo, int rows, int D, float eps,
                 const void* w, const void* b, const void* mod, int mod_rows, int shift_idx,
-                int scale_idx, int rows_per_frame, cudaStream_t stream) {
+                int scale_idx, int rows_per_frame, int row_offset, cudaStream_t stream) {
   if (D % 8 != 0 || D > kRowThreads * 8 * kMaxVec || rows <= 0 || ldx % 8 != 0 || ldo % 8 != 0) {
     set_last_error("ln_modulate: unsupported D=%d rows=%d", D, rows);
     return KR_ERR_UNSUPPORTED_SHAPE;
@@ -140,7 +140,7 @@ int ln_modulate(const void* x, int ldx, void* out, int ldo, int rows, int D, flo
   ln_modulate_kernel<<<rows, kRowThreads, 0, stream>>>(
       static_cast<const uint16_t*>(x), ldx, static_cast<uint16_t*>(out), ldo, D, eps,
       static_cast<const uint16_t*>(w), static_cast<const uint16_t*>(b),
-      static_cast<const uint16_t*>(mod), mod_rows, shift_idx, scale_idx, rows_per_frame);
+      static_cast<const uint16_t*>(mod), mod_rows, shift_idx, scale_idx, rows_per_frame, row_offset);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_last_error("ln_modulate: launch failed: %s", cudaGetErrorString(e));
@@ -182,9 +182,10 @@ __global__ void __launch_bounds__(kRowThreads) qkv_post_kernel(const QkvPostPara
   const float rk = rsqrtf(block_sum(sk, red) / p.D + p.eps);
 
   const int hw = p.grid_h * p.grid_w;
-  const int pf = row / hw + p.start_frame;
-  const int ph = (row % hw) / p.grid_w;
-  const int pw = row % p.grid_w;
+  const int grow = row + p.row_offset;
+  const int pf = grow / hw + p.start_frame;
+  const int ph = (grow % hw) / p.grid_w;
+  const int pw = grow % p.grid_w;
   const int c = p.head_dim >> 1;
   const int c_h = c / 3, c_t = c - 2 * c_h;
 

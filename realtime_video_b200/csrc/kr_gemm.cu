@@ -164,7 +164,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
       const uint16_t* gate_row = nullptr;
       if constexpr (kEpi == EPI_BIAS_GATE_RES) {
-        const int g = row_ok ? row / p.rows_per_gate : 0;
+        const int g = row_ok ? (row + p.row_offset) / p.rows_per_gate : 0;
         gate_row = reinterpret_cast<const uint16_t*>(p.gate) + static_cast<size_t>(g) * p.gate_stride;
       }
 
@@ -251,7 +251,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
               }
             }
-            uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + static_cast<size_t>(row) * p.ldc + col0;
+            uint16_t* o = (p.out2 != nullptr && col0 >= p.n_split)
+                ? reinterpret_cast<uint16_t*>(p.out2) + static_cast<size_t>(row) * p.ldc2 + (col0 - p.n_split)
+                : reinterpret_cast<uint16_t*>(p.out) + static_cast<size_t>(row) * p.ldc + col0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint4 w;
@@ -349,6 +351,10 @@ int gemm_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, 
   }
   if ((epi == EPI_BIAS_GATE_RES || epi == EPI_BIAS_RES) && p.residual == nullptr) {
     set_last_error("gemm: residual epilogue without residual pointer");
+    return KR_ERR_INVALID_ARG;
+  }
+  if (p.out2 != nullptr && (p.n_split % 256 != 0 || p.ldc2 % 8 != 0 || epi == EPI_F32)) {
+    set_last_error("gemm: split output needs n_split %% 256 == 0, ldc2 %% 8 == 0 and a 16-bit epilogue");
     return KR_ERR_INVALID_ARG;
   }
   if (epi == EPI_BIAS_GATE_RES && (p.gate == nullptr || p.rows_per_gate <= 0)) {

@@ -25,7 +25,13 @@ struct GemmParams {
   int ldr;               // elements
   int gate_stride;       // elements between consecutive gate rows
   int rows_per_gate;     // consecutive output rows sharing one gate row
+  int row_offset;        // global index of local row 0 (sequence-parallel shards): gate row = (row + row_offset) / rows_per_gate
   float alpha;
+  // optional second destination: output columns >= n_split go to out2 (column 0 = n_split),
+  // e.g. the V third of the fused QKV projection straight into the KV-cache slot
+  void* out2;
+  int ldc2;
+  int n_split;
 };
 int gemm_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, const GemmParams& p,
             cudaStream_t stream);
@@ -50,7 +56,7 @@ int attn_fwd(int dtype, const void* q, int ldq, const void* k, int ldk, const vo
 
 int ln_modulate(const void* x, int ldx, void* out, int ldo, int rows, int D, float eps,
                 const void* w, const void* b, const void* mod, int mod_rows, int shift_idx,
-                int scale_idx, int rows_per_frame, cudaStream_t stream);
+                int scale_idx, int rows_per_frame, int row_offset, cudaStream_t stream);
 
 struct QkvPostParams {
   const uint16_t* q; const uint16_t* k; const uint16_t* v;
@@ -62,6 +68,7 @@ struct QkvPostParams {
   const float2* rope;                       // may be null -> no rotation
   int D, head_dim;
   int grid_h, grid_w, start_frame;
+  int row_offset;                           // global token index of local row 0
   float eps;
 };
 int qkv_post(const QkvPostParams& p, int rows, cudaStream_t stream);

@@ -176,6 +176,7 @@ class CausalWanModel(nn.Module):
         self._rope_angles = ang
         self._rope_table: Optional[torch.Tensor] = None      # device float32 (cos, sin)
         self._ctx_cache = None                                # (key, embedded text)
+        self.sp = None          # optional parallel.SequenceParallel (single-stream multi-GPU mode)
         self.init_weights()
         self.gradient_checkpointing = False
         self.block_mask = None
@@ -205,6 +206,11 @@ class CausalWanModel(nn.Module):
         """causal_model.py:663-674 — returns the mask RULE; nothing is materialised."""
         return BlockMaskSpec(num_frames, frame_seqlen, num_frame_per_block, local_attn_size)
 
+    @property
+    def kv_cache_heads(self) -> int:
+        """Heads held by this rank's self-attention KV cache (all of them unless sequence-parallel)."""
+        return self.num_heads if self.sp is None else self.sp.local_heads(self.num_heads)
+
     def _rope(self, device) -> torch.Tensor:
         if self._rope_table is None or self._rope_table.device != device:
             a = self._rope_angles
@@ -230,58 +236,98 @@ class CausalWanModel(nn.Module):
         return out
 
     def _self_attention(self, blk: CausalWanAttentionBlock, h, grid, kv_cache, current_start, mask):
-        """causal_model.py:218-397: projections, q/k RMSNorm, RoPE, cache write, attention."""
+        """causal_model.py:218-397: projections, q/k RMSNorm, RoPE, cache write, attention.
+        The cache slot is resolved first so the fused QKV GEMM writes its V third straight into
+        the V cache (split output) and the RMSNorm+RoPE kernel writes K in place."""
         sa = blk.self_attn
-        L, D = h.shape
+        sp = self.sp
+        n_loc, D = h.shape                       # local token rows
+        L = n_loc if sp is None else n_loc * sp.world
+        r0 = 0 if sp is None else sp.rank * n_loc
+        heads = sa.num_heads if sp is None else sp.local_heads(sa.num_heads)
+        Dh = heads * sa.head_dim                 # cache row width on this rank
         f, gh, gw = grid
         fs = gh * gw
-        if sa.fused_projections:
+        kc = kv_cache["k"][0].view(-1, Dh)       # [cache_rows, heads_local*128]
+        vc = kv_cache["v"][0].view(-1, Dh)
+        kv_size = kc.shape[0]
+        if mask is not None:
+            # recompute branch (:305-348): positions 0..f-1, cache[:, :L] = K,V, block-causal mask
+            local_start, local_end, start_frame, current_end = 0, L, 0, L
+        else:
+            # cache branch (:349-392)
+            start_frame = current_start // fs
+            current_end = current_start + L
+            sink_tokens = sa.sink_size * fs
+            g_end, l_end = int(kv_cache["global_end_index"]), int(kv_cache["local_end_index"])
+            if sa.local_attn_size != -1 and current_end > g_end and L + l_end > kv_size:
+                evicted = L + l_end - kv_size
+                rolled = l_end - evicted - sink_tokens
+                for c in (kc, vc):      # left-shift the window, keeping the sink tokens (:363-373)
+                    c[sink_tokens:sink_tokens + rolled] = \
+                        c[sink_tokens + evicted:sink_tokens + evicted + rolled].clone()
+                local_end = l_end + current_end - g_end - evicted
+            else:
+                local_end = l_end + current_end - g_end
+            local_start = local_end - L
+        if local_start < 0 or local_end > kv_size:
+            raise RuntimeError(f"KV cache overflow: slot [{local_start}, {local_end}) of {kv_size}")
+        k_slot, v_slot = kc[local_start:local_end], vc[local_start:local_end]
+        if sp is not None:
+            # sequence-parallel: project / normalise / rotate MY rows (all heads), then one
+            # all-to-all per tensor turns them into ALL rows of MY heads; K and V are received
+            # straight into this rank's head-sharded cache slot
+            if sa.fused_projections:
+                qkv = ops.gemm(h, sa.to_qkv.weight, sa.to_qkv.bias)
+                q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+            else:
+                q = ops.gemm(h, sa.q.weight, sa.q.bias)
+                k = ops.gemm(h, sa.k.weight, sa.k.bias)
+                v = ops.gemm(h, sa.v.weight, sa.v.bias)
+            rq = torch.empty(n_loc, D, dtype=h.dtype, device=h.device)
+            rk = torch.empty(n_loc, D, dtype=h.dtype, device=h.device)
+            ops.qkv_norm_rope(q, k, None, sa.norm_q.weight, sa.norm_k.weight, rq, rk, None,
+                              self._rope(h.device), head_dim=sa.head_dim, grid_h=gh, grid_w=gw,
+                              start_frame=start_frame, eps=sa.eps, row_offset=r0)
+            q_full = sp.rows_to_heads(rq)
+            sp.rows_to_heads(rk, out=k_slot)
+            sp.rows_to_heads(v.contiguous(), out=v_slot)
+            kv_cache["global_end_index"] = current_end
+            kv_cache["local_end_index"] = local_end
+            if mask is not None:
+                pad = math.ceil(L / 128) * 128 - L
+                o = ops.attention(q_full, kc[:L], vc[:L], heads=heads, block_len=mask.block_len,
+                                  window=mask.window, pad_keys=pad)
+            else:
+                max_att = sa._max_attention_frames * fs if sa.local_attn_size == -1 else sa.local_attn_size * fs
+                lo = max(0, local_end - max_att)
+                o = ops.attention(q_full, kc[lo:local_end], vc[lo:local_end], heads=heads)
+            return sp.heads_to_rows(o)
+        if sa.fused_projections and (2 * D) % 256 == 0:
+            qk = torch.empty(L, 2 * D, dtype=h.dtype, device=h.device)
+            ops.gemm(h, sa.to_qkv.weight, sa.to_qkv.bias, out=qk, out2=v_slot, n_split=2 * D)
+            q, k, v = qk[:, :D], qk[:, D:], None
+        elif sa.fused_projections:
             qkv = ops.gemm(h, sa.to_qkv.weight, sa.to_qkv.bias)
             q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
         else:
             q = ops.gemm(h, sa.q.weight, sa.q.bias)
             k = ops.gemm(h, sa.k.weight, sa.k.bias)
-            v = ops.gemm(h, sa.v.weight, sa.v.bias)
-        kc = kv_cache["k"][0].view(-1, D)        # [cache_rows, D]
-        vc = kv_cache["v"][0].view(-1, D)
+            ops.gemm(h, sa.v.weight, sa.v.bias, out=v_slot)
+            v = None
         rq = torch.empty(L, D, dtype=h.dtype, device=h.device)
-        rope = self._rope(h.device)
+        ops.qkv_norm_rope(q, k, v, sa.norm_q.weight, sa.norm_k.weight, rq, k_slot,
+                          v_slot if v is not None else None, self._rope(h.device), head_dim=sa.head_dim,
+                          grid_h=gh, grid_w=gw, start_frame=start_frame, eps=sa.eps)
+        kv_cache["global_end_index"] = current_end
+        kv_cache["local_end_index"] = local_end
         if mask is not None:
-            # recompute branch (:305-348): positions 0..f-1, cache[:, :L] = K,V, block-causal mask
-            ops.qkv_norm_rope(q, k, v, sa.norm_q.weight, sa.norm_k.weight, rq, kc[:L], vc[:L], rope,
-                              head_dim=sa.head_dim, grid_h=gh, grid_w=gw, start_frame=0, eps=sa.eps)
-            kv_cache["global_end_index"] = L
-            kv_cache["local_end_index"] = L
             pad = math.ceil(L / 128) * 128 - L
             return ops.attention(rq, kc[:L], vc[:L], heads=sa.num_heads, block_len=mask.block_len,
                                  window=mask.window, pad_keys=pad)
-        # cache branch (:349-392)
-        start_frame = current_start // fs
-        current_end = current_start + L
-        sink_tokens = sa.sink_size * fs
-        kv_size = kc.shape[0]
-        g_end, l_end = int(kv_cache["global_end_index"]), int(kv_cache["local_end_index"])
-        if sa.local_attn_size != -1 and current_end > g_end and L + l_end > kv_size:
-            evicted = L + l_end - kv_size
-            rolled = l_end - evicted - sink_tokens
-            for c in (kc, vc):      # left-shift the window, keeping the sink tokens (:363-373)
-                c[sink_tokens:sink_tokens + rolled] = \
-                    c[sink_tokens + evicted:sink_tokens + evicted + rolled].clone()
-            local_end = l_end + current_end - g_end - evicted
-        else:
-            local_end = l_end + current_end - g_end
-        local_start = local_end - L
-        if local_start < 0 or local_end > kv_size:
-            raise RuntimeError(f"KV cache overflow: slot [{local_start}, {local_end}) of {kv_size}")
-        ops.qkv_norm_rope(q, k, v, sa.norm_q.weight, sa.norm_k.weight, rq, kc[local_start:local_end],
-                          vc[local_start:local_end], rope, head_dim=sa.head_dim, grid_h=gh, grid_w=gw,
-                          start_frame=start_frame, eps=sa.eps)
         max_att = sa._max_attention_frames * fs if sa.local_attn_size == -1 else sa.local_attn_size * fs
         lo = max(0, local_end - max_att)
-        out = ops.attention(rq, kc[lo:local_end], vc[lo:local_end], heads=sa.num_heads)
-        kv_cache["global_end_index"] = current_end
-        kv_cache["local_end_index"] = local_end
-        return out
+        return ops.attention(rq, kc[lo:local_end], vc[lo:local_end], heads=sa.num_heads)
 
     def _cross_attention(self, blk: CausalWanAttentionBlock, h, ctx, cache):
         """wan/modules/model.py:171-228 (K/V of the prompt computed once, cached by assignment)."""
@@ -306,12 +352,14 @@ class CausalWanModel(nn.Module):
                current_start, mask):
         """causal_model.py:440-492; x [L, D] is updated in place."""
         fs = grid[1] * grid[2]
+        r0 = 0 if self.sp is None else self.sp.rank * x.shape[0]       # global index of my first row
         emod = ops.add_modulation(blk.modulation, e0)                    # [F, 6, D]
-        h = ops.ln_modulate(x, eps=blk.eps, mod=emod, shift_idx=0, scale_idx=1, rows_per_frame=fs)
+        h = ops.ln_modulate(x, eps=blk.eps, mod=emod, shift_idx=0, scale_idx=1, rows_per_frame=fs,
+                            row_offset=r0)
         y = self._self_attention(blk, h, grid, kv_cache, current_start, mask)
         sa = blk.self_attn
         ops.gemm(y, sa.o.weight, sa.o.bias, epilogue=ops.EPI_BIAS_GATE_RES, residual=x,
-                 gate=emod[:, 2], rows_per_gate=fs, out=x)
+                 gate=emod[:, 2], rows_per_gate=fs, out=x, row_offset=r0)
         n3 = blk.norm3
         if isinstance(n3, nn.LayerNorm):
             h = ops.ln_modulate(x, eps=n3.eps, weight=n3.weight, bias=n3.bias, out=h)
@@ -320,10 +368,11 @@ class CausalWanModel(nn.Module):
         y = self._cross_attention(blk, h, ctx, crossattn_cache)
         ca = blk.cross_attn
         ops.gemm(y, ca.o.weight, ca.o.bias, epilogue=ops.EPI_BIAS_RES, residual=x, out=x)
-        h = ops.ln_modulate(x, eps=blk.eps, mod=emod, shift_idx=3, scale_idx=4, rows_per_frame=fs, out=h)
+        h = ops.ln_modulate(x, eps=blk.eps, mod=emod, shift_idx=3, scale_idx=4, rows_per_frame=fs, out=h,
+                            row_offset=r0)
         hid = ops.gemm(h, blk.ffn[0].weight, blk.ffn[0].bias, epilogue=ops.EPI_BIAS_GELU)
         ops.gemm(hid, blk.ffn[2].weight, blk.ffn[2].bias, epilogue=ops.EPI_BIAS_GATE_RES, residual=x,
-                 gate=emod[:, 5], rows_per_gate=fs, out=x)
+                 gate=emod[:, 5], rows_per_gate=fs, out=x, row_offset=r0)
         return x
 
     # ----------------------------------------------------------------------------------------
@@ -335,6 +384,10 @@ class CausalWanModel(nn.Module):
         C, Fr, H, W = x.shape
         grid = (Fr, H // self.patch_size[1], W // self.patch_size[2])
         tok = ops.patchify(x.to(dt))
+        r0 = 0
+        if self.sp is not None:                      # my contiguous share of the token rows
+            r0, n_loc = self.sp.rows(tok.shape[0])
+            tok = tok[r0:r0 + n_loc]
         pw = self.patch_embedding.weight.view(self.dim, -1)
         xs = ops.gemm(tok, pw, self.patch_embedding.bias)                                   # [L, D]
         # time embeddings (causal_model.py:888-892): sinusoid in fp64 (model.py:15-24), bf16 MLPs
@@ -355,8 +408,11 @@ class CausalWanModel(nn.Module):
         # head (causal_model.py:512-523, :951)
         fs = grid[1] * grid[2]
         ehead = ops.add_modulation(self.head.modulation, e.view(Fr, 1, self.dim).expand(Fr, 2, self.dim).contiguous())
-        h = ops.ln_modulate(xs, eps=self.head.eps, mod=ehead, shift_idx=0, scale_idx=1, rows_per_frame=fs)
+        h = ops.ln_modulate(xs, eps=self.head.eps, mod=ehead, shift_idx=0, scale_idx=1, rows_per_frame=fs,
+                            row_offset=r0)
         out = ops.gemm(h, self.head.head.weight, self.head.head.bias)
+        if self.sp is not None:
+            out = self.sp.gather_rows(out)           # every rank needs the full latent for the next step
         return out, grid
 
     def _forward_inference(self, x, t, context, seq_len, clip_fea=None, y=None, kv_cache=None,

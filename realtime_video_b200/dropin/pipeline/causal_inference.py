@@ -170,9 +170,10 @@ class CausalInferencePipeline(torch.nn.Module):
             kv_cache_size = self.local_attn_size * self.frame_seq_length
         else:
             kv_cache_size = 21 * self.frame_seq_length      # 32760 at 1560 tokens/frame (:289)
-        num_heads = self.generator.model.config.num_heads
-        dim = self.generator.model.config.dim
-        shape = [batch_size, kv_cache_size, num_heads, dim // num_heads]
+        head_dim = self.generator.model.config.dim // self.generator.model.config.num_heads
+        # sequence-parallel runs keep only this rank's heads (realtime_video_b200/parallel.py)
+        num_heads = getattr(self.generator.model, "kv_cache_heads", self.generator.model.config.num_heads)
+        shape = [batch_size, kv_cache_size, num_heads, head_dim]
         if self.kv_cache1 and list(self.kv_cache1[0]["k"].shape) == shape:
             for c in self.kv_cache1:
                 if self.zero_kv_on_reset:

@@ -103,8 +103,10 @@ def _rows2d(t: torch.Tensor, name: str):
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
          epilogue: int = EPI_BIAS, out: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
-         rows_per_gate: int = 0, alpha: float = 1.0) -> torch.Tensor:
-    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T + bias).  gate: [G, N] rows (pitch = stride(0))."""
+         rows_per_gate: int = 0, alpha: float = 1.0, out2: Optional[torch.Tensor] = None,
+         n_split: int = 0, row_offset: int = 0) -> torch.Tensor:
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T + bias).  gate: [G, N] rows (pitch = stride(0)).
+    out2: rows-strided [M, N - n_split] destination of the output columns >= n_split."""
     _req(a, "a"); _req(w, "w", a.dtype)
     M, lda = _rows2d(a, "a")
     K = a.shape[-1]
@@ -123,11 +125,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     if gate is not None:
         _req(gate, "gate", a.dtype)
         gs = gate.stride(0) if gate.dim() >= 2 else 0
+    ldc2 = 0
+    if out2 is not None:
+        _req(out2, "out2", a.dtype)
+        _, ldc2 = _rows2d(out2, "out2")
     lib = _lib.load()
     with _Timed("gemm", 2.0 * M * N * K):
         rc = lib.kr_gemm(_DT[a.dtype], epilogue, a.data_ptr(), lda, w.data_ptr(), w.stride(0),
                          _ptr(bias), out.data_ptr(), ldc, M, N, K, _ptr(residual), ldr, _ptr(gate), gs,
-                         rows_per_gate, alpha, _stream())
+                         rows_per_gate, alpha, _ptr(out2), ldc2, n_split, row_offset, _stream())
     _lib.check(rc, "kr_gemm")
     _count()
     return out
@@ -164,7 +170,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, heads: int,
 def ln_modulate(x: torch.Tensor, *, eps: float, weight: Optional[torch.Tensor] = None,
                 bias: Optional[torch.Tensor] = None, mod: Optional[torch.Tensor] = None,
                 shift_idx: int = 0, scale_idx: int = 1, rows_per_frame: int = 0,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, row_offset: int = 0) -> torch.Tensor:
     """LayerNorm over the last dim (+affine) (+ x*(1+mod[f,scale_idx]) + mod[f,shift_idx])."""
     _req(x, "x", torch.bfloat16)
     rows, ldx = _rows2d(x, "x")
@@ -181,14 +187,14 @@ def ln_modulate(x: torch.Tensor, *, eps: float, weight: Optional[torch.Tensor] =
     lib = _lib.load()
     rc = lib.kr_ln_modulate(x.data_ptr(), ldx, out.data_ptr(), ldo, rows, D, eps, _ptr(weight),
                             _ptr(bias), _ptr(mod), mod_rows, shift_idx, scale_idx, rows_per_frame,
-                            _stream())
+                            row_offset, _stream())
     _lib.check(rc, "kr_ln_modulate")
     _count()
     return out
 
 
 def qkv_norm_rope(q, k, v, wq, wk, q_out, k_out, v_out, rope, *, head_dim: int, grid_h: int,
-                  grid_w: int, start_frame: int, eps: float) -> None:
+                  grid_w: int, start_frame: int, eps: float, row_offset: int = 0) -> None:
     """RMSNorm(q), RMSNorm(k), RoPE, write q_out / K-cache slot / V-cache slot (row views)."""
     _req(q, "q", torch.bfloat16)
     rows, ldq = _rows2d(q, "q")
@@ -204,7 +210,7 @@ def qkv_norm_rope(q, k, v, wq, wk, q_out, k_out, v_out, rope, *, head_dim: int, 
     rc = lib.kr_qkv_norm_rope(q.data_ptr(), ldq, k.data_ptr(), ldk, _ptr(v), ldv, wq.data_ptr(),
                               wk.data_ptr(), q_out.data_ptr(), ldqo, k_out.data_ptr(), ldko,
                               _ptr(v_out), ldvo, _ptr(rope), rows, D, head_dim, grid_h, grid_w,
-                              start_frame, eps, _stream())
+                              start_frame, row_offset, eps, _stream())
     _lib.check(rc, "kr_qkv_norm_rope")
     _count()
 

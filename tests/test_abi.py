@@ -42,7 +42,8 @@ def test_version_and_error_string(lib):
 
 def test_argument_validation_needs_no_gpu(lib):
     """Bad arguments are rejected before any CUDA call: codes are negative, message is set."""
-    rc = lib.kr_gemm(0, 0, None, 0, None, 0, None, None, 0, 1, 1, 1, None, 0, None, 0, 0, ctypes.c_float(1.0), None)
+    rc = lib.kr_gemm(0, 0, None, 0, None, 0, None, None, 0, 1, 1, 1, None, 0, None, 0, 0, ctypes.c_float(1.0), None, 0, 0,
+                     0, None)
     assert rc == -1 and b"null" in lib.kr_last_error()
     rc = lib.kr_attn_fwd(5, None, 0, None, 0, None, 0, None, 0, 1, 1, 1, ctypes.c_float(1.0), 0, 0, 0, 0, None)
     assert rc == -1
