@@ -16,7 +16,7 @@ from pathlib import Path
 _PKG_DIR = Path(__file__).resolve().parent
 _CSRC = _PKG_DIR / "csrc"
 LIB_PATH = _PKG_DIR / "libkrea_b200.so"
-SOURCES = ["kr_host.cu", "kr_gemm.cu", "kr_attn.cu", "kr_dit_elem.cu", "kr_vae.cu", "kr_api.cu"]
+SOURCES = ["kr_host.cu", "kr_gemm.cu", "kr_gemm2.cu", "kr_attn.cu", "kr_dit_elem.cu", "kr_vae.cu", "kr_api.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -21,6 +21,8 @@
 #include "kr_common.cuh"
 #include "kr_ops.h"
 
+#include <cstdlib>
+
 namespace kr {
 
 
@@ -112,40 +114,42 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc<kBf16>(BLOCK_M, BLOCK_N, 0, 0);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-      for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    // ===================== MMA issuer: ONE thread runs the whole loop =====================
+    // (a warp-wide wait + elect + __syncwarp per k-block left the tensor pipe idle ~25 % of the time:
+    //  the issue loop, not operand delivery, was the limiter — profiles/r01_ncu_gemm_ffn1.txt)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<kBf16>(BLOCK_M, BLOCK_N, 0, 0);
+      const uint64_t desc_hi = make_smem_desc(0, 16, 1024) & 0xFFFFFFFF00000000ull;
+      const uint32_t desc_lo_c = static_cast<uint32_t>(make_smem_desc(0, 16, 1024));
+      const uint32_t a0 = smem_u32(smem_a), b0 = smem_u32(smem_b);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
-          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_lo = desc_lo_c | (((a0 + stage * Cfg::kABytes) & 0x3FFFF) >> 4);
+          const uint32_t b_lo = desc_lo_c | (((b0 + stage * Cfg::kBBytes) & 0x3FFFF) >> 4);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t a_desc = make_smem_desc(a_addr + k * UMMA_K * 2, 16, 1024);
-            const uint64_t b_desc = make_smem_desc(b_addr + k * UMMA_K * 2, 16, 1024);
-            umma_ss(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_ss(d_tmem, desc_hi | (a_lo + k * 2), desc_hi | (b_lo + k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
           if (kb == num_k - 1) umma_commit(&tmem_full[acc]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        __syncwarp();
-        if (++stage == Cfg::kStages) {
-          stage = 0;
-          phase ^= 1;
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
         }
-      }
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
       }
     }
   } else {
@@ -361,6 +365,12 @@ int gemm_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, 
     set_last_error("gemm: gate epilogue without gate pointer / rows_per_gate");
     return KR_ERR_INVALID_ARG;
   }
+  // wide projections: CTA-pair kernel (KR_GEMM2=0 disables it)
+  // KR_GEMM2: 0 = never, 1 = where its wave efficiency wins (default), 2 = whenever N % 256 == 0 (tests)
+  static const int g2_mode = [] { const char* e = getenv("KR_GEMM2"); return e != nullptr ? atoi(e) : 1; }();
+  if (g2_mode > 0 && epi != EPI_F32 && p.N % 256 == 0 &&
+      (g2_mode == 2 || gemm2_preferred(p.M, p.N, p.K)))
+    return gemm2_tn(dtype, epi, a, lda, w, ldw, p, stream);
   int bn;
   if (p.N % 256 == 0) bn = 256;
   else if (p.N % 128 == 0) bn = 128;

@@ -35,6 +35,10 @@ struct GemmParams {
 };
 int gemm_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, const GemmParams& p,
             cudaStream_t stream);
+// CTA-pair (cta_group::2, 256x256 tiles) variant, kr_gemm2.cu
+int gemm2_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, const GemmParams& p,
+             cudaStream_t stream);
+bool gemm2_preferred(int M, int N, int K);
 
 struct AttnParams {
   void* out;           // [Lq, heads*128] 16-bit

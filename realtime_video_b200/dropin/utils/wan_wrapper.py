@@ -210,23 +210,30 @@ class WanDiffusionWrapper(nn.Module):
 
 
 class WanVAEWrapper(nn.Module):
-    """utils/wan_wrapper.py:58-118 — classic-path VAE (decode_to_pixel / encode_to_latent)."""
+    """utils/wan_wrapper.py:58-118 — classic-path VAE.  ``self.model`` carries the reference's
+    ``decoder.*`` / ``conv2.*`` state-dict keys (the decoder half of WanVAE_); decode runs on the
+    sm_100a engine in the latent dtype (bf16 on the classic path, wan_wrapper.py:102-104)."""
 
-    def __init__(self, *args, **kwargs):
+    def __init__(self):
         super().__init__()
-        from realtime_video_b200.vae import WanVAEDecoderCore   # lazy: VAE kernels
-        self.mean = torch.tensor(WanVAEDecoderCore.MEAN, dtype=torch.float32)
-        self.std = torch.tensor(WanVAEDecoderCore.STD, dtype=torch.float32)
-        self.core = WanVAEDecoderCore(*args, **kwargs)
+        from realtime_video_b200.vae import MEAN, STD, VAEDecoderWrapper
+        self.mean = torch.tensor(MEAN, dtype=torch.float32)
+        self.std = torch.tensor(STD, dtype=torch.float32)
+        self.model = VAEDecoderWrapper()
+        self._cache = [None] * 55
 
     def decode_to_pixel(self, latent: torch.Tensor, use_cache: bool = False) -> torch.Tensor:
-        """latent [B, F, 16, h, w] -> pixels [B, F', 3, H, W] fp32 in [-1, 1]."""
+        """latent [B, F, 16, h, w] -> pixels [B, F', 3, H, W] fp32 in [-1, 1]
+        (use_cache=False: fresh stream per call = WanVAE_.decode, vae.py:519-543;
+         use_cache=True: WanVAE_.cached_decode, vae.py:545-567, batch 1)."""
+        if use_cache:
+            assert latent.shape[0] == 1, "Batch size must be 1 when using cache"
         outs = []
         for b in range(latent.shape[0]):
-            cache = self.core.persistent_cache if use_cache else [None] * self.core.num_cache_slots
-            px, cache = self.core.decode(latent[b:b + 1], cache)
+            cache = self._cache if use_cache else [None] * 55
+            px, cache = self.model(latent[b:b + 1], *cache)
             if use_cache:
-                self.core.persistent_cache = cache
+                self._cache = cache
             outs.append(px[0])
         return torch.stack(outs)
 

@@ -500,16 +500,3 @@ class VAEDecoderWrapperSingle(nn.Module):
         if self._engine is None:
             self._engine = DecoderEngine(self.decoder, self.conv2, self.mean, self.std, single_mode=True)
         return self._engine.decode_single(z, is_first_frame, list(feat_cache))
-
-
-class WanVAEDecoderCore:
-    """Decoder used by the classic-path ``WanVAEWrapper`` (utils/wan_wrapper.py:58-118)."""
-    MEAN, STD = MEAN, STD
-
-    def __init__(self, wrapper: Optional[VAEDecoderWrapper] = None):
-        self.wrapper = wrapper if wrapper is not None else VAEDecoderWrapper()
-        self.num_cache_slots = 55
-        self.persistent_cache: List[Optional[torch.Tensor]] = [None] * 55
-
-    def decode(self, latent, cache):
-        return self.wrapper(latent, *cache)
