@@ -284,7 +284,8 @@ def main():
     K, W = args.steps, args.warmup
     transformer = factory.synthetic_transformer("14B", device=dev, num_layers=args.layers, seed=0)
     vae = factory.synthetic_vae_decoder(device=dev)
-    models = factory.build_models(transformer, vae_decoder=vae, device=dev)
+    vae_enc = factory.synthetic_vae_encoder(device=dev)
+    models = factory.build_models(transformer, vae_decoder=vae, device=dev, vae_encoder=vae_enc)
     pe = factory.synthetic_prompt_embeds(device=dev)
 
     def barrier():
@@ -398,8 +399,9 @@ def main():
         "config": {"workload": WORKLOAD, "model_dims": "Wan2.1-T2V-14B (40 layers, d 5120, ffn 13824, 40 heads)"
                    if args.layers == LAYERS else f"DEBUG {args.layers} layers",
                    "resolution": "832x480", "denoise_steps": 4, "kv_cache_num_frames": 3, "frames_per_step": 12,
-                   "passes_per_step": "1 KV recompute + 4 denoise DiT passes + VAE decode (fp16)",
-                   "first_frame": "kept (reference keep_first_frame=True; VAE-encoder re-encode is a 'next' row)",
+                   "passes_per_step": "1-frame VAE encode + 1 KV recompute + 4 denoise DiT passes + VAE decode (fp16)",
+                   "first_frame": "re-encoded from the oldest cached pixel frame once the window slides "
+                                  "(reference default keep_first_frame=False, release_server.py:571-576)",
                    "parallelism": "1 GPU" if world == 1 else (
                        f"ONE stream, Ulysses sequence parallel over {world} GPUs (rows<->heads all-to-all, NCCL); "
                        f"VAE decode on rank 0" if sp_mode else f"{world} independent replicas (path does not shard)"),

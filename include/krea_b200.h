@@ -118,12 +118,15 @@ int kr_unpatchify_x0(const void* head_out, int ldh, const void* xt, const double
  * one.  tile_w*tile_h == 128.  Outputs (any subset), element strides per pixel / per frame:
  *   out_raw  = cast(acc + bias [+ residual])
  *   out_norm = SiLU(RMS_norm_C(out_raw) * sqrt(cout) * gamma)     (vae.py:39-54, :184-186)
- *   out_pix  = clamp(out_raw, -1, 1) as fp32 [T, cout, H, W]       (vae_block3.py:226) */
+ *   out_pix  = clamp(out_raw, -1, 1) as fp32 [T, cout, H, W]       (vae_block3.py:226)
+ * sub2 = 1: the encoder's stride-2 Conv2d behind ZeroPad2d((0,1,0,1)) (vae.py:84-92): only the odd
+ * (h, w) positions of the stride-1 result are kept, compacted to an H/2 x W/2 output.
+ * Extra (cin, n) pairs for the encoder: (64,96) (96,192) (384,32). */
 int kr_vae_conv3d(int dtype, int cin, int n, const void* in, int t_in, const void* weight,
                   int w_rows, const void* bias, int cout, int T, int H, int W, int tile_w, int tile_h,
                   int kt, int kh, int kw, void* out_raw, long raw_pix, long raw_frame, void* out_norm,
                   long norm_pix, long norm_frame, const void* gamma, const void* residual,
-                  long res_pix, long res_frame, float* out_pix, void* stream);
+                  long res_pix, long res_frame, float* out_pix, int sub2, void* stream);
 
 /* y = RMS_norm_C(x) * sqrt(C) * gamma [-> SiLU], x,y [pixels, C]  (vae.py:39-54) */
 int kr_vae_rmsnorm_silu(int dtype, const void* x, void* y, const void* gamma, long pixels, int C,

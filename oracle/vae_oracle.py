@@ -133,3 +133,42 @@ class VAEDecoderOracle:
 
 
 from realtime_video_b200.factory import synthetic_vae_params  # noqa: E402,F401  (seeded weights, shared)
+
+
+class VAEEncoderOracle:
+    """First-chunk encode (one pixel frame, empty cache): demo_utils/vae_block3.py:136-150,
+    wan/modules/vae.py:301-345 (Encoder3d.forward), :144-172 (Resample downsample: the
+    downsample3d time_conv is skipped while its cache slot is None), WanVAE_.conv1 + chunk +
+    (mu - mean) * 1/std (vae_block3.py:166-172).  Params keyed 'encoder.*', 'conv1.*'."""
+
+    def __init__(self, params):
+        self.p = params
+        self.dec = VAEDecoderOracle(params)     # reuses causal-conv / res / attention restatements
+
+    def encode_first(self, x):
+        """x [1, 3, 1, H, W] -> mu [1, 16, 1, H/8, W/8]."""
+        p, d = self.p, self.dec
+        cache, idx = {}, [0]
+        x = d._cached_conv("encoder.conv1", x, cache, idx)
+        n = 0
+        for i in range(4):
+            for _ in range(2):
+                x = d._res(f"encoder.downsamples.{n}", x, cache, idx)
+                n += 1
+            if i != 3:
+                pre = f"encoder.downsamples.{n}"
+                b, c, t, h, w = x.shape
+                y = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w)
+                y = F.conv2d(F.pad(y, (0, 1, 0, 1)), p[pre + ".resample.1.weight"], p[pre + ".resample.1.bias"], stride=2)
+                x = y.reshape(b, t, c, h // 2, w // 2).permute(0, 2, 1, 3, 4)
+                n += 1          # first chunk: downsample3d only stores its cache (vae.py:160-163)
+        x = d._res("encoder.middle.0", x, cache, idx)
+        x = d._attn("encoder.middle.1", x)
+        x = d._res("encoder.middle.2", x, cache, idx)
+        x = F.silu(rms_norm(x, p["encoder.head.0.gamma"]))
+        x = d._cached_conv("encoder.head.2", x, cache, idx)
+        mu = causal_conv3d(x, p["conv1.weight"], p["conv1.bias"]).chunk(2, dim=1)[0]
+        dt = mu.dtype
+        mean = torch.tensor(MEAN, dtype=torch.float32).to(dt).view(1, 16, 1, 1, 1)
+        inv_std = (1.0 / torch.tensor(STD, dtype=torch.float32).to(dt)).view(1, 16, 1, 1, 1)
+        return (mu - mean) * inv_std

@@ -103,7 +103,7 @@ SIGNATURES = {
     "kr_patchify": [_vp, _l, _l, _l, _l, _vp, _i, _i, _i, _i, _vp],
     "kr_unpatchify_x0": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "kr_vae_conv3d": [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _l, _l,
-                      _vp, _l, _l, _vp, _vp, _l, _l, _vp, _vp],
+                      _vp, _l, _l, _vp, _vp, _l, _l, _vp, _i, _vp],
     "kr_vae_rmsnorm_silu": [_i, _vp, _vp, _vp, _l, _i, _i, _vp],
     "kr_vae_upsample2x": [_vp, _vp, _i, _i, _i, _i, _vp],
     "kr_vae_scale_input": [_i, _vp, _l, _l, _l, _l, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],

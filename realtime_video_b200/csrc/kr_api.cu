@@ -112,7 +112,7 @@ int kr_vae_conv3d(int dtype, int cin, int n, const void* in, int t_in, const voi
                   int w_rows, const void* bias, int cout, int T, int H, int W, int tile_w, int tile_h,
                   int kt, int kh, int kw, void* out_raw, long raw_pix, long raw_frame, void* out_norm,
                   long norm_pix, long norm_frame, const void* gamma, const void* residual,
-                  long res_pix, long res_frame, float* out_pix, void* stream) {
+                  long res_pix, long res_frame, float* out_pix, int sub2, void* stream) {
   KR_REQUIRE(in && weight, "null input/weight");
   KR_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (bf16) or 1 (fp16)");
   KR_REQUIRE(out_raw || out_norm || out_pix, "no output requested");
@@ -123,7 +123,7 @@ int kr_vae_conv3d(int dtype, int cin, int n, const void* in, int t_in, const voi
   p.out_norm = out_norm; p.norm_pix = norm_pix; p.norm_frame = norm_frame;
   p.out_pix = out_pix; p.bias = bias;
   p.residual = residual; p.res_pix = res_pix; p.res_frame = res_frame;
-  p.gamma = gamma; p.norm_scale = sqrtf(static_cast<float>(cout));
+  p.gamma = gamma; p.norm_scale = sqrtf(static_cast<float>(cout)); p.sub2 = sub2;
   return kr::vae_conv(dtype, cin, n, in, t_in, weight, w_rows, p, static_cast<cudaStream_t>(stream));
 }
 

@@ -97,6 +97,7 @@ struct ConvParams {
   const void* residual; long res_pix, res_frame;
   const void* gamma;                            // [cout] for out_norm
   float norm_scale;                             // sqrt(C)
+  int sub2;                                     // 1: keep only odd (h, w) outputs, compacted to H/2 x W/2
 };
 int vae_conv(int dtype, int cin, int n, const void* in, int t_in, const void* wgt, int w_rows,
              const ConvParams& p, cudaStream_t stream);

@@ -171,22 +171,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in64, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc<kBf16>(128, Cfg::kMmaN, 0, 0);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    const int k_stages = taps * Cfg::kStagesPerTap;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
-      for (int ks = 0; ks < k_stages; ++ks) {
-        mbar_wait(&full_bar[stage], phase);
+    // ===================== MMA issuer: ONE thread runs the whole loop =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<kBf16>(128, Cfg::kMmaN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const int k_stages = taps * Cfg::kStagesPerTap;
+      const uint32_t smem0 = smem_u32(smem);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t st = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
+        for (int ks = 0; ks < k_stages; ++ks) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem0 + stage * Cfg::kStageBytes;
           const uint32_t a64 = st, b64 = st + Cfg::kA64;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -212,16 +213,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in64, const __grid_cons
           }
           umma_commit(&empty_bar[stage]);
           if (ks == k_stages - 1) umma_commit(&tmem_full[acc]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        __syncwarp();
-        if (++stage == Cfg::kStages) {
-          stage = 0;
-          phase ^= 1;
+        if (++acc == Cfg::kNumAcc) {
+          acc = 0;
+          acc_phase ^= 1;
         }
-      }
-      if (++acc == Cfg::kNumAcc) {
-        acc = 0;
-        acc_phase ^= 1;
       }
     }
   } else {
@@ -237,8 +237,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in64, const __grid_cons
       const int rem = tile % tiles_per_frame;
       const int h = (rem / tiles_w) * p.TH + r / p.TW;
       const int w = (rem % tiles_w) * p.TW + r % p.TW;
-      const bool ok = h < p.H && w < p.W;
-      const long pix = static_cast<long>(h) * p.W + w;
+      // sub2: stride-2 convolution with right/bottom zero pad (ZeroPad2d((0,1,0,1)) + Conv2d(stride 2),
+      // vae.py:84-92) evaluated as the stride-1 conv at the odd positions: out(i,j) = full(2i+1, 2j+1)
+      const bool ok = h < p.H && w < p.W && (p.sub2 == 0 || ((h & 1) && (w & 1)));
+      const long pix = p.sub2 ? static_cast<long>(h >> 1) * (p.W >> 1) + (w >> 1)
+                              : static_cast<long>(h) * p.W + w;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * Cfg::kAccStride;
@@ -459,6 +462,9 @@ static int dispatch_conv(int cin, int n, const void* in, int t_in, const void* w
   KR_CONV_CASE(192, 96)
   KR_CONV_CASE(96, 96)
   KR_CONV_CASE(96, 16)
+  KR_CONV_CASE(64, 96)
+  KR_CONV_CASE(96, 192)
+  KR_CONV_CASE(384, 32)
 #undef KR_CONV_CASE
   set_last_error("vae_conv: unsupported channel configuration cin=%d n=%d", cin, n);
   return KR_ERR_UNSUPPORTED_SHAPE;

@@ -48,14 +48,15 @@ def pipeline_args(denoising_step_list=(1000, 750, 500, 250), num_frame_per_block
                                  context_noise=0, model_kwargs={})
 
 
-def build_models(transformer: WanDiffusionWrapper, vae_decoder=None, text_encoder=None, device="cuda") -> Models:
+def build_models(transformer: WanDiffusionWrapper, vae_decoder=None, text_encoder=None, device="cuda",
+                 vae_encoder=None) -> Models:
     pipe = CausalInferencePipeline(pipeline_args(), device=device, generator=transformer,
                                    text_encoder=text_encoder if text_encoder is not None else object(),
                                    vae=vae_decoder if vae_decoder is not None else object())
-    return Models(text_encoder, transformer, pipe, None, vae_decoder)
+    return Models(text_encoder, transformer, pipe, vae_encoder, vae_decoder)
 
 
-def synthetic_vae_params(seed: int = 0, dim: int = 96, z_dim: int = 16):
+def synthetic_vae_params(seed: int = 0, dim: int = 96, z_dim: int = 16, encoder: bool = False):
     """Deterministic decoder weights independent of module construction order: every tensor is
     drawn from its own generator seeded by (seed, key).  Conv weights ~ N(0, 1/fan_in) * 1.4,
     biases ~ N(0, .02), gammas ~ 1 + N(0, .1)."""
@@ -103,6 +104,35 @@ def synthetic_vae_params(seed: int = 0, dim: int = 96, z_dim: int = 16):
             n += 1
     shapes["decoder.head.0.gamma"] = (dims[4], 1, 1, 1)
     conv3("decoder.head.2", dims[4], 3, (3, 3, 3))
+    if encoder:
+        # Encoder3d (wan/modules/vae.py:254-299) + WanVAE_.conv1 (:471): keys 'encoder.*', 'conv1.*'
+        shapes = {k: v for k, v in shapes.items() if False}
+        edims = [dim, dim, dim * 2, dim * 4, dim * 4]
+        conv3("conv1", 2 * z_dim, 2 * z_dim, (1, 1, 1))
+        conv3("encoder.conv1", 3, edims[0], (3, 3, 3))
+        n = 0
+        for i, (ci, co) in enumerate(zip(edims[:-1], edims[1:])):
+            for _ in range(2):
+                res(f"encoder.downsamples.{n}", ci, co)
+                ci = co
+                n += 1
+            if i != 3:
+                pre = f"encoder.downsamples.{n}"
+                shapes[pre + ".resample.1.weight"] = (co, co, 3, 3)
+                shapes[pre + ".resample.1.bias"] = (co,)
+                if i >= 1:                      # temperal_downsample = [False, True, True]
+                    conv3(pre + ".time_conv", co, co, (3, 1, 1))
+                n += 1
+        top = edims[-1]
+        res("encoder.middle.0", top, top)
+        shapes["encoder.middle.1.norm.gamma"] = (top, 1, 1)
+        shapes["encoder.middle.1.to_qkv.weight"] = (3 * top, top, 1, 1)
+        shapes["encoder.middle.1.to_qkv.bias"] = (3 * top,)
+        shapes["encoder.middle.1.proj.weight"] = (top, top, 1, 1)
+        shapes["encoder.middle.1.proj.bias"] = (top,)
+        res("encoder.middle.2", top, top)
+        shapes["encoder.head.0.gamma"] = (top, 1, 1, 1)
+        conv3("encoder.head.2", top, 2 * z_dim, (3, 3, 3))
     out = {}
     for k, shp in shapes.items():
         g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(k.encode())) % (2 ** 31))
@@ -125,4 +155,12 @@ def synthetic_vae_decoder(device="cuda", dtype=torch.float16, seed: int = 0):
     from .vae import VAEDecoderWrapper
     m = VAEDecoderWrapper()
     m.load_state_dict(synthetic_vae_params(seed=seed), strict=False)
+    return m.to(device=device, dtype=dtype).eval().requires_grad_(False)
+
+
+def synthetic_vae_encoder(device="cuda", dtype=torch.float16, seed: int = 0):
+    """VAEEncoderWrapper (demo_utils/vae_block3.py:116) with seeded synthetic weights."""
+    from .vae import VAEEncoderWrapper
+    m = VAEEncoderWrapper()
+    m.load_state_dict(synthetic_vae_params(seed=seed, encoder=True), strict=False)
     return m.to(device=device, dtype=dtype).eval().requires_grad_(False)

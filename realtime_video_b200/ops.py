@@ -300,7 +300,7 @@ def vae_conv(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]
              T: int, taps, tile, out_raw: Optional[torch.Tensor] = None,
              out_norm: Optional[torch.Tensor] = None, gamma: Optional[torch.Tensor] = None,
              residual: Optional[torch.Tensor] = None, out_pix: Optional[torch.Tensor] = None,
-             raw_frame_stride: Optional[int] = None) -> None:
+             raw_frame_stride: Optional[int] = None, sub2: bool = False) -> None:
     """x [t_in, H, W, cin] (t_in >= T + kt - 1, cached frames in front); weight [rows, taps*cin].
 
     out_raw / out_norm / residual: channels-last frame stacks [>=T, H, W, C]; ``raw_frame_stride``
@@ -315,7 +315,8 @@ def vae_conv(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]
     def strides(t):
         if t is None:
             return None, 0, 0
-        if t.stride(-1) != 1 or t.stride(-3) != W * t.stride(-2):
+        wo = W // 2 if sub2 else W
+        if t.stride(-1) != 1 or t.stride(-3) != wo * t.stride(-2):
             raise _lib.KreaB200Error("vae_conv: outputs must be channels-last with dense rows")
         return t.data_ptr(), t.stride(-2), t.stride(0)
 
@@ -329,7 +330,7 @@ def vae_conv(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]
     with _Timed("vae_conv", _fl):
       rc = lib.kr_vae_conv3d(_DT[x.dtype], cin, n, x.data_ptr(), t_in, weight.data_ptr(), weight.shape[0],
                            _ptr(bias), cout, T, H, W, tw, th, kt, kh, kw, rp, rpix, rfr, npr, npix, nfr,
-                           _ptr(gamma), sp, spix, sfr, _ptr(out_pix), _stream())
+                           _ptr(gamma), sp, spix, sfr, _ptr(out_pix), 1 if sub2 else 0, _stream())
     _lib.check(rc, "kr_vae_conv3d")
     _count()
 

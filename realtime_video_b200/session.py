@@ -9,9 +9,10 @@ Per block (release_server.py:636-736):
     N denoise steps     -> DiT pass, flow->x0, re-noise with the session RNG (bf16 randn)
     VAE decode          -> pixels [1, 12 (9 for block 0), 3, H, W] fp32 in [-1, 1]
 Webcam / v2v / prompt interpolation / start-frame are caller features outside the hot path.
-The first-frame RE-ENCODE of a slid window (release_server.py:571-576) needs the VAE encoder
-("next" row): until that lands the session keeps the first latent frame
-(the reference's own ``keep_first_frame=True`` behaviour, release_server.py:566-570).
+Once the context window slides, the reference re-encodes the oldest cached PIXEL frame into the first
+context latent (release_server.py:571-576): done here with the sm_100a VAE encoder
+(``realtime_video_b200.vae.VAEEncoderWrapper``) when ``models.vae_encoder`` is given; without an encoder
+(or with ``keep_first_frame=True``) the first latent frame is kept (release_server.py:566-570).
 """
 from __future__ import annotations
 
@@ -36,7 +37,7 @@ class GenerateParams:
     num_denoising_steps: int = 4
     timestep_shift: float = 5.0
     strength: float = 1.0
-    keep_first_frame: bool = True
+    keep_first_frame: bool = False
     context_noise: float = 0.0
 
 
@@ -59,6 +60,7 @@ class GenerationSession:
     def __init__(self, params: GenerateParams, models: Models, prompt_embeds: Optional[torch.Tensor] = None,
                  device=None, decode: bool = True):
         self.params, self.models, self.decode = params, models, decode
+        self.decode_enabled = decode or getattr(models.pipeline.generator.model, "sp", None) is not None
         self.gpu = torch.device(device if device is not None else "cuda")
         self.width, self.height = params.width // 8 * 8, params.height // 8 * 8
         self.latent_width, self.latent_height = self.width // 8, self.height // 8
@@ -95,13 +97,31 @@ class GenerationSession:
         st = p.scheduler.timesteps
         self.zero_padded_timesteps = torch.cat((st.cpu(), torch.tensor([0], dtype=torch.float32))).to(self.gpu)
 
-    # release_server.py:563-576 (keep_first_frame behaviour; see module docstring)
+    # release_server.py:563-576
     def get_clean_context_frames(self):
         kvn = self.params.kv_cache_num_frames
+        nfpb = self.models.pipeline.num_frame_per_block
         ctx = self.all_latents[:, :self.current_start_frame]
-        if kvn == 1:
-            return ctx[:, :1]
-        return torch.cat((ctx[:, :1], ctx[:, 1:][:, -kvn + 1:]), dim=1)
+        keep = self.params.keep_first_frame or self.models.vae_encoder is None or not self.decode_enabled
+        if keep or (self.block_idx - 1) * nfpb < kvn:
+            if kvn == 1:
+                return ctx[:, :1]
+            return torch.cat((ctx[:, :1], ctx[:, 1:][:, -kvn + 1:]), dim=1)
+        # window has slid: first context latent = re-encoded oldest cached pixel frame
+        ctx = ctx[:, 1:][:, -kvn + 1:]
+        first = None
+        if self.decode:
+            frame = self.frame_context_cache[0][0].half()                 # [1, 3, H, W]
+            z = frame.transpose(0, 1).unsqueeze(0)                        # [1, 3, 1, H, W] (v2v.py:138-158)
+            mu, _ = self.models.vae_encoder(z, [None] * 55, stream=False)
+            first = mu.squeeze(0).to(torch.float16).transpose(0, 1)[None].to(self.all_latents)   # [1,1,16,h,w]
+        sp = getattr(self.models.pipeline.generator.model, "sp", None)
+        if sp is not None:                                                # one stream on several GPUs
+            import torch.distributed as dist
+            if first is None:
+                first = torch.empty_like(ctx[:, :1])
+            dist.broadcast(first, src=0, group=sp.group)
+        return torch.cat((first, ctx), dim=1)
 
     # release_server.py:588-633
     def recompute_kv_cache(self):

@@ -59,13 +59,18 @@ class Upsample(nn.Upsample):
 
 class Resample(nn.Module):
     def __init__(self, dim, mode):
-        assert mode in ("upsample2d", "upsample3d")
+        assert mode in ("upsample2d", "upsample3d", "downsample2d", "downsample3d")
         super().__init__()
         self.dim, self.mode, self.cache_t = dim, mode, 2
-        self.resample = nn.Sequential(Upsample(scale_factor=(2., 2.), mode="nearest"),
-                                      nn.Conv2d(dim, dim // 2, 3, padding=1))
-        if mode == "upsample3d":
-            self.time_conv = CausalConv3d(dim, dim * 2, (3, 1, 1), padding=(1, 0, 0))
+        if mode.startswith("up"):
+            self.resample = nn.Sequential(Upsample(scale_factor=(2., 2.), mode="nearest"),
+                                          nn.Conv2d(dim, dim // 2, 3, padding=1))
+            if mode == "upsample3d":
+                self.time_conv = CausalConv3d(dim, dim * 2, (3, 1, 1), padding=(1, 0, 0))
+        else:   # wan/modules/vae.py:84-92
+            self.resample = nn.Sequential(nn.ZeroPad2d((0, 1, 0, 1)), nn.Conv2d(dim, dim, 3, stride=(2, 2)))
+            if mode == "downsample3d":
+                self.time_conv = CausalConv3d(dim, dim, (3, 1, 1), stride=(2, 1, 1), padding=(0, 0, 0))
 
 
 class ResidualBlock(nn.Module):
@@ -153,6 +158,26 @@ def _prep_conv(w: torch.Tensor, b: torch.Tensor, dtype, device, cin_pad=None, n_
     bp = torch.zeros(max(n_pad, 32), dtype=dtype, device=device)
     bp[:cout] = b.to(device=device, dtype=dtype)
     return _Conv(wp.reshape(n_pad, kt * kh * kw * cin_pad).contiguous(), bp, cin_pad, n_pad, cout, (kt, kh, kw))
+
+
+def _vae_attention(b, x):
+    """vae.py:229-251 — per frame single-head attention over H*W tokens, C channels."""
+    T, H, W, C = x.shape
+    L = H * W
+    if L % 32 != 0:
+        raise NotImplementedError(f"VAE attention: H*W={L} must be a multiple of 32")
+    out = torch.empty_like(x)
+    xn = ops.vae_rmsnorm_silu(x, b["g"], torch.empty_like(x), silu=False)
+    for t in range(T):
+        xt, xnt = x[t].view(L, C), xn[t].view(L, C)
+        qkv = ops.gemm(xnt, b["wqkv"], b["bqkv"])
+        q, k = qkv[:, :C], qkv[:, C:2 * C]
+        s = ops.gemm(q, k, None, epilogue=ops.EPI_F32, alpha=1.0 / math.sqrt(C))      # [L, L] fp32
+        p = ops.softmax_rows(s, torch.empty(L, L, dtype=x.dtype, device=x.device))
+        vt = ops.gemm(b["wqkv"][2 * C:], xnt, None)                                       # V^T [C, L]
+        o = ops.gemm(p, vt, b["bqkv"][2 * C:])       # softmax rows sum to 1: P(V + 1 b^T) = PV + b^T
+        ops.gemm(o, b["wproj"], b["bproj"], epilogue=ops.EPI_BIAS_RES, residual=xt, out=out[t].view(L, C))
+    return out
 
 
 class DecoderEngine:
@@ -286,23 +311,7 @@ class DecoderEngine:
         return torch.empty(t, h, w, c, dtype=self.dtype, device=self.device)
 
     def _attention(self, b, x):
-        """vae.py:229-251 — per frame single-head attention over H*W tokens, C channels."""
-        T, H, W, C = x.shape
-        L = H * W
-        if L % 32 != 0:
-            raise NotImplementedError(f"VAE attention: H*W={L} must be a multiple of 32")
-        out = torch.empty_like(x)
-        xn = ops.vae_rmsnorm_silu(x, b["g"], torch.empty_like(x), silu=False)
-        for t in range(T):
-            xt, xnt = x[t].view(L, C), xn[t].view(L, C)
-            qkv = ops.gemm(xnt, b["wqkv"], b["bqkv"])
-            q, k = qkv[:, :C], qkv[:, C:2 * C]
-            s = ops.gemm(q, k, None, epilogue=ops.EPI_F32, alpha=1.0 / math.sqrt(C))      # [L, L] fp32
-            p = ops.softmax_rows(s, torch.empty(L, L, dtype=x.dtype, device=x.device))
-            vt = ops.gemm(b["wqkv"][2 * C:], xnt, None)                                       # V^T [C, L]
-            o = ops.gemm(p, vt, b["bqkv"][2 * C:])       # softmax rows sum to 1: P(V + 1 b^T) = PV + b^T
-            ops.gemm(o, b["wproj"], b["bproj"], epilogue=ops.EPI_BIAS_RES, residual=xt, out=out[t].view(L, C))
-        return out
+        return _vae_attention(b, x)
 
     # -- decode a chunk of latent frames -----------------------------------------------------
     def decode_chunk(self, z: torch.Tensor, first: bool) -> torch.Tensor:
@@ -500,3 +509,168 @@ class VAEDecoderWrapperSingle(nn.Module):
         if self._engine is None:
             self._engine = DecoderEngine(self.decoder, self.conv2, self.mean, self.std, single_mode=True)
         return self._engine.decode_single(z, is_first_frame, list(feat_cache))
+
+
+# ---------------------------------------------------------------------------------------------
+# encoder (first-chunk path): the first-frame re-encode of the server loop
+# ---------------------------------------------------------------------------------------------
+class Encoder3d(nn.Module):
+    """wan/modules/vae.py:254-299 (module tree only; temperal_downsample=[False, True, True])."""
+
+    def __init__(self, dim=96, z_dim=32, dim_mult=[1, 2, 4, 4], num_res_blocks=2,
+                 temperal_downsample=[False, True, True], dropout=0.0):
+        super().__init__()
+        dims = [dim * u for u in [1] + dim_mult]
+        self.conv1 = CausalConv3d(3, dims[0], 3, padding=1)
+        downs = []
+        for i, (in_dim, out_dim) in enumerate(zip(dims[:-1], dims[1:])):
+            for _ in range(num_res_blocks):
+                downs.append(ResidualBlock(in_dim, out_dim, dropout))
+                in_dim = out_dim
+            if i != len(dim_mult) - 1:
+                downs.append(Resample(out_dim, mode="downsample3d" if temperal_downsample[i] else "downsample2d"))
+        self.downsamples = nn.Sequential(*downs)
+        self.middle = nn.Sequential(ResidualBlock(out_dim, out_dim, dropout), AttentionBlock(out_dim),
+                                    ResidualBlock(out_dim, out_dim, dropout))
+        self.head = nn.Sequential(RMS_norm(out_dim, images=False), nn.SiLU(),
+                                  CausalConv3d(out_dim, z_dim, 3, padding=1))
+
+
+class EncoderEngine:
+    """Encoder3d + WanVAE_.conv1 + latent scaling on the sm_100a kernels, FIRST CHUNK only:
+    one pixel frame with an empty feature cache (vae_block3.py:136-150 with feat_cache[0] is None) —
+    every causal conv sees zero history and the downsample3d time_convs are skipped (vae.py:160-163).
+    That is exactly the server's first-frame re-encode (release_server.py:571-576)."""
+
+    def __init__(self, encoder: Encoder3d, conv1: nn.Module, mean: torch.Tensor, std: torch.Tensor):
+        self.encoder, self.conv1_mod, self.mean, self.std = encoder, conv1, mean, std
+        self._key = None
+
+    def _prepare(self, dtype, device, H, W):
+        e = self.encoder
+        key = (dtype, str(device), H, W, e.conv1.weight._version, e.conv1.weight.data_ptr())
+        if self._key == key:
+            return
+        pc = lambda m, **kw: _prep_conv(m.weight.data, m.bias.data, dtype, device, **kw)  # noqa: E731
+        g = lambda n: n.gamma.data.reshape(-1).to(device=device, dtype=dtype).contiguous()  # noqa: E731
+        self.dtype, self.device, self.H, self.W = dtype, device, H, W
+        self.conv_in = pc(e.conv1, cin_pad=64)
+        self.blocks = []
+        for m in list(e.downsamples) + list(e.middle):
+            if isinstance(m, ResidualBlock):
+                r = m.residual
+                self.blocks.append(dict(kind="res", g1=g(r[0]), c1=pc(r[2]), g2=g(r[3]), c2=pc(r[6]),
+                                        sc=pc(m.shortcut) if isinstance(m.shortcut, nn.Conv3d) else None,
+                                        cin=m.in_dim, cout=m.out_dim))
+            elif isinstance(m, AttentionBlock):
+                C = m.dim
+                self.blocks.append(dict(
+                    kind="attn", g=g(m.norm), C=C,
+                    wqkv=m.to_qkv.weight.data.reshape(3 * C, C).to(device=device, dtype=dtype).contiguous(),
+                    bqkv=m.to_qkv.bias.data.to(device=device, dtype=dtype).contiguous(),
+                    wproj=m.proj.weight.data.reshape(C, C).to(device=device, dtype=dtype).contiguous(),
+                    bproj=m.proj.bias.data.to(device=device, dtype=dtype).contiguous()))
+            else:
+                self.blocks.append(dict(kind="down", C=m.dim, conv=pc(m.resample[1])))
+        self.g_head = g(e.head[0])
+        self.head = pc(e.head[2])
+        self.w_out = self.conv1_mod.weight.data.reshape(32, 32).to(device=device, dtype=dtype).contiguous()
+        self.b_out = self.conv1_mod.bias.data.to(device=device, dtype=dtype).contiguous()
+        self.mean_d = self.mean.to(device=device, dtype=dtype)
+        self.inv_std_d = 1.0 / self.std.to(device=device, dtype=dtype)
+        # conv-input buffers [2 zero history frames + 1 frame]
+        z = lambda h, w, c: torch.zeros(3, h, w, c, dtype=dtype, device=device)  # noqa: E731
+        self.conv_in.buf = z(H, W, 64)
+        h, w = H, W
+        for b in self.blocks:
+            if b["kind"] == "res":
+                b["c1"].buf, b["c2"].buf = z(h, w, b["cin"]), z(h, w, b["cout"])
+            elif b["kind"] == "down":
+                h, w = h // 2, w // 2
+        self.head.buf = z(h, w, self.head.cin)
+        self._key = key
+
+    def _conv(self, c: _Conv, src=None, **kw):
+        x = c.buf if src is None else src
+        ops.vae_conv(x, c.weight, c.bias, n=c.n, cout=c.cout, T=1, taps=c.taps,
+                     tile=_tile_for(x.shape[1], x.shape[2]), **kw)
+
+    def encode_first(self, frame: torch.Tensor) -> torch.Tensor:
+        """frame [3, H, W] in [-1, 1] -> mu [16, H/8, W/8] (scaled latent), dtype of the engine."""
+        dt, dev = self.dtype, self.device
+        H, W = self.H, self.W
+        new = lambda h, w, c: torch.empty(1, h, w, c, dtype=dt, device=dev)  # noqa: E731
+        cin = self.conv_in
+        cin.buf[2, :, :, :3] = frame.to(dt).permute(1, 2, 0)
+        blocks = self.blocks
+
+        def next_norm(i):
+            if i + 1 < len(blocks):
+                nb = blocks[i + 1]
+                return (nb["g1"], nb["c1"]) if nb["kind"] == "res" else (None, None)
+            return self.g_head, self.head
+
+        h, w = H, W
+        x = new(h, w, cin.cout)
+        self._conv(cin, out_raw=x, out_norm=blocks[0]["c1"].buf[2:3], gamma=blocks[0]["g1"])
+        for i, b in enumerate(blocks):
+            if b["kind"] == "res":
+                res = x
+                if b["sc"] is not None:
+                    res = new(h, w, b["cout"])
+                    self._conv(b["sc"], src=x, out_raw=res)
+                self._conv(b["c1"], out_norm=b["c2"].buf[2:3], gamma=b["g2"])
+                g, nxt = next_norm(i)
+                need_raw = nxt is not self.head
+                xo = new(h, w, b["cout"]) if need_raw else None
+                self._conv(b["c2"], residual=res, out_raw=xo,
+                           out_norm=nxt.buf[2:3] if g is not None else None, gamma=g)
+                x = xo
+            elif b["kind"] == "attn":
+                x = _vae_attention(b, x)
+                nb = blocks[i + 1]
+                ops.vae_rmsnorm_silu(x, nb["g1"], nb["c1"].buf[2:3])
+            else:   # downsample: stride-2 conv behind ZeroPad2d((0,1,0,1)); first chunk skips time_conv
+                g, nxt = next_norm(i)
+                xo = new(h // 2, w // 2, b["C"])
+                self._conv(b["conv"], src=x, out_raw=xo, out_norm=nxt.buf[2:3], gamma=g, sub2=True)
+                x, h, w = xo, h // 2, w // 2
+        y = new(h, w, self.head.cout)
+        self._conv(self.head, out_raw=y)
+        out = ops.gemm(y.view(h * w, self.head.cout), self.w_out, self.b_out)           # WanVAE_.conv1 (1x1x1)
+        mu = out[:, :16]
+        mu = (mu - self.mean_d.view(1, 16)) * self.inv_std_d.view(1, 16)               # vae_block3.py:168-172
+        return mu.t().reshape(16, h, w)
+
+
+class VAEEncoderWrapper(nn.Module):
+    """demo_utils/vae_block3.py:116-175 for the first-chunk case: ``forward(z [1,3,1,H,W],
+    feat_cache (all None), stream=False) -> (mu [1,16,1,H/8,W/8], feat_cache)``.  Streaming
+    encodes of later chunks (v2v / webcam) are not implemented and raise."""
+
+    def __init__(self, vae=None):
+        super().__init__()
+        self.encoder = Encoder3d()
+        self.conv1 = CausalConv3d(32, 32, 1)
+        if vae is not None:       # reference signature: take the weights of a loaded WanVAE
+            self.encoder.load_state_dict(vae.model.encoder.state_dict())
+            self.conv1.load_state_dict(vae.model.conv1.state_dict())
+        self.register_buffer("mean", torch.tensor(MEAN, dtype=torch.float32))
+        self.register_buffer("std", torch.tensor(STD, dtype=torch.float32))
+        self.z_dim = 16
+        self._engine: Optional[EncoderEngine] = None
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def forward(self, z: torch.Tensor, feat_cache, stream: bool = False):
+        if z.shape[0] != 1 or z.shape[2] != 1 or any(c is not None for c in feat_cache) or stream:
+            raise NotImplementedError("B200 VAE encoder: only the first chunk (one frame, empty cache) is "
+                                      "implemented; streaming / multi-chunk encode is a 'next' row")
+        if self._engine is None:
+            self._engine = EncoderEngine(self.encoder, self.conv1, self.mean, self.std)
+        dtype = z.dtype if z.dtype in (torch.float16, torch.bfloat16) else torch.float16
+        self._engine._prepare(dtype, z.device, z.shape[-2], z.shape[-1])
+        mu = self._engine.encode_first(z[0, :, 0])
+        return mu[None, :, None], feat_cache

@@ -62,10 +62,32 @@ def run_single(tag, h, w):
         print(tag, i, tuple(px.shape), float(px.abs().mean()), flush=True)
 
 
+@torch.no_grad()
+def run_encoder(tag, H, W):
+    """demo_utils.vae_block3.VAEEncoderWrapper on ONE pixel frame with an empty cache (the server's
+    first-frame re-encode, release_server.py:571-576)."""
+    import types
+    ns = ref_shim.install()
+    m = ns.vae.WanVAE_(dim=96, z_dim=16, dim_mult=[1, 2, 4, 4], num_res_blocks=2, attn_scales=[],
+                       temperal_downsample=[False, True, True], dropout=0.0)
+    missing = m.load_state_dict(synthetic_vae_params(seed=0, encoder=True), strict=False)
+    assert not missing.unexpected_keys
+    m = m.float().eval()
+    enc = ns.vae_block3.VAEEncoderWrapper(types.SimpleNamespace(model=m)).float().eval()
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(1, 3, 1, H, W, generator=g) * 2 - 1
+    mu, _ = enc(x, [None] * 55)
+    OUT[f"{tag}/x"] = x.numpy()
+    OUT[f"{tag}/mu"] = mu.numpy()
+    print(tag, tuple(mu.shape), float(mu.abs().mean()), flush=True)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     run("s8x12", 8, 12, 1)
     run("s16x24", 16, 24, 2)
     run_single("single8x12", 8, 12)
+    run_encoder("enc64x96", 64, 96)
+    run_encoder("enc128x192", 128, 192)
     np.savez_compressed(HERE / "vae_small.npz", **OUT)
     print("vae_small.npz", sum(v.nbytes for v in OUT.values()) / 1e6, "MB raw")

@@ -19,3 +19,14 @@ def test_decoder_oracle_matches_reference(tag, sub):
             assert px.shape[1] == expect_frames[call]
             r = rel_l2(px[..., ::sub, ::sub], g[f"{tag}/px{call}"])
             assert r < 2e-5, f"{tag} call {call}: rel_l2={r:.3e}"
+
+
+@pytest.mark.parametrize("tag", ["enc64x96", "enc128x192"])
+def test_encoder_oracle_matches_reference(tag):
+    from oracle.vae_oracle import VAEEncoderOracle
+    g = load_npz("vae_small.npz")
+    orc = VAEEncoderOracle(synthetic_vae_params(seed=0, encoder=True))
+    with torch.no_grad():
+        mu = orc.encode_first(g[f"{tag}/x"])
+    assert mu.shape == g[f"{tag}/mu"].shape
+    assert rel_l2(mu, g[f"{tag}/mu"]) < 2e-5

@@ -97,3 +97,20 @@ def test_single_frame_wrapper_vs_reference_golden():
             ref = g[f"single8x12/px{i}"]
             r = rel_l2(px.float().cpu(), ref)
             assert r < 2e-2, f"single frame {i}: rel_l2={r:.3e}"
+
+
+@pytest.mark.parametrize("tag", ["enc64x96", "enc128x192"])
+def test_encoder_first_frame_vs_reference_golden(tag):
+    """First-frame re-encode (release_server.py:571-576): fp16 engine vs the fp32 reference.
+    Tolerance: rel-L2 <= 2e-2 on the scaled latent."""
+    from realtime_video_b200.vae import VAEEncoderWrapper
+    g = load_npz("vae_small.npz")
+    m = VAEEncoderWrapper()
+    m.load_state_dict(synthetic_vae_params(seed=0, encoder=True), strict=False)
+    m = m.to(device="cuda", dtype=torch.float16).eval()
+    with torch.no_grad():
+        mu, cache = m(g[f"{tag}/x"].cuda().half(), [None] * 55)
+    ref = g[f"{tag}/mu"]
+    assert mu.shape == ref.shape
+    r = rel_l2(mu, ref)
+    assert r < 2e-2, f"{tag}: rel_l2={r:.3e}"
