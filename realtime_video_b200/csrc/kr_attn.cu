@@ -37,7 +37,7 @@ static constexpr int kHalfBytes = kTileBytes / 2;           // one 64-column swi
 static constexpr int kAttnThreads = 384;
 static constexpr int kAttnSmem = 2 * kTileBytes + kKvStages * kTileBytes + 1024 + 256;
 
-template <bool kBf16, bool kPHalf>
+template <bool kBf16, bool kPHalf, bool kPolyExp>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -365,8 +365,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         float b1 = fast_exp2(fmaf(__uint_as_float(r1[2 * c + 1]), sl2, nms));
         float c0 = fast_exp2(fmaf(__uint_as_float(r2[2 * c]), sl2, nms));
         float c1 = fast_exp2(fmaf(__uint_as_float(r2[2 * c + 1]), sl2, nms));
-        float d0 = fast_exp2(fmaf(__uint_as_float(r3[2 * c]), sl2, nms));
-        float d1 = fast_exp2(fmaf(__uint_as_float(r3[2 * c + 1]), sl2, nms));
+        // the last quarter of the tile goes through the polynomial (FMA pipe) instead of the MUFU
+        float d0 = kPolyExp ? poly_exp2(fmaf(__uint_as_float(r3[2 * c]), sl2, nms))
+                            : fast_exp2(fmaf(__uint_as_float(r3[2 * c]), sl2, nms));
+        float d1 = kPolyExp ? poly_exp2(fmaf(__uint_as_float(r3[2 * c + 1]), sl2, nms))
+                            : fast_exp2(fmaf(__uint_as_float(r3[2 * c + 1]), sl2, nms));
         rowsum += (a0 + a1) + (b0 + b1) + (c0 + c1) + (d0 + d1);
         pk[c] = kBf16 ? pack_bf16x2(a0, a1) : pack_f16x2(a0, a1);
         pk[16 + c] = kBf16 ? pack_bf16x2(b0, b1) : pack_f16x2(b0, b1);
@@ -455,8 +458,13 @@ int attn_fwd(int dtype, const void* q, int ldq, const void* k, int ldk, const vo
   // KR_ATTN_P_F16=1 selects the experimental fp16-P softmax (exp on f16x2) instead of the default
   // bf16-P one (fp32 exp per element, P rounded to the KV dtype like FlashAttention-2)
   static const bool p_f16 = [] { const char* e = getenv("KR_ATTN_P_F16"); return e != nullptr && e[0] == '1'; }();
-  auto kern = bf ? (p_f16 ? attn_fwd_kernel<true, true> : attn_fwd_kernel<true, false>)
-                 : attn_fwd_kernel<false, false>;
+  // KR_ATTN_POLY=1 moves a quarter of the exponentials to an FMA-pipe polynomial (FlashAttention-4 style).
+  // Measured on B200 (r01): 966 TF/s with it vs 1100 TF/s without at Lq 4680 / Lkv 9360 — the softmax
+  // warps are issue-bound, not MUFU-bound, so it stays off by default.
+  static const bool poly = [] { const char* e = getenv("KR_ATTN_POLY"); return e != nullptr && e[0] == '1'; }();
+  auto kern = bf ? (p_f16 ? attn_fwd_kernel<true, true, false>
+                          : (poly ? attn_fwd_kernel<true, false, true> : attn_fwd_kernel<true, false, false>))
+                 : (poly ? attn_fwd_kernel<false, false, true> : attn_fwd_kernel<false, false, false>);
   static bool attr_set[2] = {false, false};
   if (!attr_set[bf ? 0 : 1]) {   // (p_f16 is process-constant, so one flag per dtype suffices)
     cudaError_t e =
