@@ -19,6 +19,24 @@
 // TMEM (512 cols): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P (16-bit) aliases the
 // first 64 columns of its S buffer and feeds the P.V MMA as the TMEM A operand.
 // Online softmax with lazy rescaling (O is only rescaled when the running max grows by > 2^8).
+// P is handed to the MMA warp in kParts column slices (one mbarrier each, one elected arrive per warp):
+// P.V over the first keys of a tile can start while the warpgroup still exponentiates the rest.
+// The TMA and MMA roles run in ONE elected thread each (elect.sync, not `lane == 0`: ptxas then emits
+// UTCHMMA / UTCBAR / UTMALDG back to back instead of wrapping each in an ELECT/branch loop).
+//
+// Where the time goes (ncu, Lq 4680 / Lkv 9360 / 40 heads, r01): tensor pipe 58 %, XU (MUFU) 59 %,
+// ~3440 clk per 128 keys against 2048 clk of MMA and 2048 clk of MUFU work.  The two warpgroups are a
+// two-customer closed queue over two servers (MUFU 16 ex2/clk/SM, tensor pipe) plus ~700 clk of
+// per-tile latency (TMEM load, max, store, barrier round trips); mean-value analysis of that queue
+// gives 3500 clk.  Variants measured on B200 and NOT kept (git history has them):
+//   * 1 / 2 / 4 hand-over slices: 1125 / 1128 / 1129 TF/s;  f32x2-packed FFMA/FADD: 1091 TF/s
+//   * quarter of the exponentials as an FMA-pipe cubic (FlashAttention-4 style): 966 TF/s
+//   * fp16 P with ex2.approx.f16x2: SASS is MUFU.EX2.F16 per element (no MUFU saving)
+//   * one 128-row tile per CTA, S double-buffered, warpgroups splitting each tile by columns
+//     (named barrier per tile): 1021 TF/s — the barrier puts both warps of a scheduler in lock step,
+//     so their MUFU phases coincide instead of interleaving, and K/V L2->SM traffic doubles
+//   * two tiles per CTA, 64-key tiles with two S buffers per tile (softmax never waits for P.V):
+//     1052 TF/s — 24 MMAs of 32-64 clk per 64 keys make the single issuing thread the limiter
 #include "kr_common.cuh"
 #include "kr_ops.h"
 
@@ -37,7 +55,9 @@ static constexpr int kHalfBytes = kTileBytes / 2;           // one 64-column swi
 static constexpr int kAttnThreads = 384;
 static constexpr int kAttnSmem = 2 * kTileBytes + kKvStages * kTileBytes + 1024 + 256;
 
-template <bool kBf16, bool kPHalf, bool kPolyExp>
+static constexpr int kParts = 2;   // P hand-over slices (1, 2 and 4 measured within 0.5 % of each other)
+
+template <bool kBf16>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -51,9 +71,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* kv_full = bars + 1;            // [kKvStages]
   uint64_t* kv_empty = kv_full + kKvStages;   // [kKvStages]
   uint64_t* s_full = kv_empty + kKvStages;    // [2]
-  uint64_t* p_ready = s_full + 2;          // [2]
-  uint64_t* o_final = p_ready + 2;         // [1]
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_final + 1);
+  uint64_t* p_ready = s_full + 2;          // [2][kParts]
+  uint64_t* o_final = p_ready + 2 * kParts;   // [1]
+  uint64_t* o_done = o_final + 1;             // [1] single-tile mode: one phase per P.V(j)
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_done + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -98,9 +119,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&s_full[i], 1);
-        mbar_init(&p_ready[i], 128);
+        for (int q = 0; q < kParts; ++q) mbar_init(&p_ready[i * kParts + q], 4);   // one arrive per warp
       }
       mbar_init(o_final, 1);
+      mbar_init(o_done, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -113,7 +135,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       const int col = head * kHeadDim;
       mbar_expect_tx(q_full, 2 * kTileBytes);
       for (int t = 0; t < 2; ++t)
@@ -140,8 +162,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_qk = make_idesc<kBf16>(128, 128, 0, 0);   // A,B K-major
-    // P.V: A = P from TMEM (fp16 when kPHalf, else the KV dtype), B = V MN-major in the KV dtype
-    constexpr uint32_t idesc_pv = make_idesc_ab(128, 128, (kPHalf || !kBf16) ? 0u : 1u, kBf16 ? 1u : 0u, 0, 1);
+    // P.V: A = P from TMEM (KV dtype), B = V MN-major in the KV dtype
+    constexpr uint32_t idesc_pv = make_idesc_ab(128, 128, kBf16 ? 1u : 0u, kBf16 ? 1u : 0u, 0, 1);
     const uint32_t q_addr = smem_u32(smem_q);
     const uint32_t kv_addr = smem_u32(smem_kv);
     const uint32_t tS[2] = {tmem_base + 0, tmem_base + 128};
@@ -158,54 +180,53 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 idesc_qk, k != 0 ? 1u : 0u);
       }
     };
-    // O buffer `ob` += P (16-bit, aliasing S buffer `sb`) . V(stage)
-    auto issue_pv = [&](int ob, int sb, int stage, bool first) {
+    // O buffer `ob` += P (16-bit, aliasing S buffer `sb`) . V(stage); each slice of P is consumed as
+    // soon as its mbarrier (phase `par`) completes.
+    auto issue_pv = [&](int ob, int sb, int stage, bool first, uint32_t par) {
       const uint32_t b = kv_addr + stage * kTileBytes;
+      constexpr int kSteps = kTileKV / 16 / kParts;
 #pragma unroll
-      for (int k = 0; k < kTileKV / 16; ++k) {
-        // P: 16 keys = 8 TMEM columns per k-step; V: 16 key rows of 128 B per panel
-        umma_ts(tO[ob], tS[sb] + k * 8, make_smem_desc(b + k * 2048, kHalfBytes, 1024), idesc_pv,
-                (first && k == 0) ? 0u : 1u);
+      for (int part = 0; part < kParts; ++part) {
+        mbar_wait(&p_ready[sb * kParts + part], par);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < kSteps; ++kk) {
+          const int k = part * kSteps + kk;
+          // P: 16 keys = 8 TMEM columns per k-step; V: 16 key rows of 128 B per panel
+          umma_ts(tO[ob], tS[sb] + k * 8, make_smem_desc(b + k * 2048, kHalfBytes, 1024), idesc_pv,
+                  (first && k == 0) ? 0u : 1u);
+        }
       }
     };
     // ring items: K_j = 2j, V_j = 2j + 1
     auto st = [](int item) { return item % kKvStages; };
     auto ph = [](int item) { return static_cast<uint32_t>((item / kKvStages) & 1); };
 
-    mbar_wait(q_full, 0);
-    if (two) {
-      // ---- two query tiles: ping-pong between the softmax warpgroups ----
-      mbar_wait(&kv_full[st(0)], ph(0));
-      tc_fence_after();
-      if (lane == 0) {
+    // one thread runs the whole issue loop (waits included): no warp-wide polling next to the softmax
+    // warps that share this scheduler
+    if (elect_one()) {
+      mbar_wait(q_full, 0);
+      if (two) {
+        // ---- two query tiles: ping-pong between the softmax warpgroups ----
+        mbar_wait(&kv_full[st(0)], ph(0));
+        tc_fence_after();
         issue_qk(0, 0, st(0));
         umma_commit(&s_full[0]);
         issue_qk(1, 1, st(0));
         umma_commit(&s_full[1]);
         umma_commit(&kv_empty[st(0)]);
-      }
-      __syncwarp();
-      for (int j = 0; j < n_tiles; ++j) {
-        const int vi = 2 * j + 1, ki = 2 * j + 2;
-        const bool more = (j + 1 < n_tiles);
-        mbar_wait(&kv_full[st(vi)], ph(vi));   // V_j
-        mbar_wait(&p_ready[0], j & 1);
-        tc_fence_after();
-        if (lane == 0) issue_pv(0, 0, st(vi), j == 0);
-        __syncwarp();
-        if (more) {
-          mbar_wait(&kv_full[st(ki)], ph(ki));   // K_{j+1}
-          tc_fence_after();
-          if (lane == 0) {
+        for (int j = 0; j < n_tiles; ++j) {
+          const int vi = 2 * j + 1, ki = 2 * j + 2;
+          const bool more = (j + 1 < n_tiles);
+          mbar_wait(&kv_full[st(vi)], ph(vi));   // V_j
+          issue_pv(0, 0, st(vi), j == 0, j & 1);
+          if (more) {
+            mbar_wait(&kv_full[st(ki)], ph(ki));   // K_{j+1}
+            tc_fence_after();
             issue_qk(0, 0, st(ki));
             umma_commit(&s_full[0]);
           }
-          __syncwarp();
-        }
-        mbar_wait(&p_ready[1], j & 1);
-        tc_fence_after();
-        if (lane == 0) {
-          issue_pv(1, 1, st(vi), j == 0);
+          issue_pv(1, 1, st(vi), j == 0, j & 1);
           umma_commit(&kv_empty[st(vi)]);
           if (more) {
             issue_qk(1, 1, st(ki));
@@ -213,52 +234,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             umma_commit(&kv_empty[st(ki)]);
           }
         }
-        __syncwarp();
-      }
-    } else {
-      // ---- one query tile (last CTA of a head): S double-buffered so Q.K_{j+1}^T overlaps softmax(j) ----
-      mbar_wait(&kv_full[st(0)], ph(0));
-      tc_fence_after();
-      if (lane == 0) {
+      } else {
+        // ---- one query tile (last CTA of a head): S double-buffered so Q.K_{j+1}^T overlaps softmax(j) ----
+        mbar_wait(&kv_full[st(0)], ph(0));
+        tc_fence_after();
         issue_qk(0, 0, st(0));
         umma_commit(&s_full[0]);
         umma_commit(&kv_empty[st(0)]);
-      }
-      __syncwarp();
-      if (n_tiles > 1) {
-        mbar_wait(&kv_full[st(2)], ph(2));
-        tc_fence_after();
-        if (lane == 0) {
+        if (n_tiles > 1) {
+          mbar_wait(&kv_full[st(2)], ph(2));
+          tc_fence_after();
           issue_qk(0, 1, st(2));
           umma_commit(&s_full[1]);
           umma_commit(&kv_empty[st(2)]);
         }
-        __syncwarp();
-      }
-      for (int j = 0; j < n_tiles; ++j) {
-        const int vi = 2 * j + 1, ki = 2 * (j + 2);
-        const int sb = j & 1;
-        mbar_wait(&kv_full[st(vi)], ph(vi));   // V_j
-        mbar_wait(&p_ready[sb], (j >> 1) & 1);
-        tc_fence_after();
-        if (lane == 0) {
-          issue_pv(0, sb, st(vi), j == 0);
+        for (int j = 0; j < n_tiles; ++j) {
+          const int vi = 2 * j + 1, ki = 2 * (j + 2);
+          const int sb = j & 1;
+          mbar_wait(&kv_full[st(vi)], ph(vi));   // V_j
+          issue_pv(0, sb, st(vi), j == 0, (j >> 1) & 1);
           umma_commit(&kv_empty[st(vi)]);
-        }
-        __syncwarp();
-        if (j + 2 < n_tiles) {
-          mbar_wait(&kv_full[st(ki)], ph(ki));   // K_{j+2}
-          tc_fence_after();
-          if (lane == 0) {
+          umma_commit(o_done);
+          if (j + 2 < n_tiles) {
+            mbar_wait(&kv_full[st(ki)], ph(ki));   // K_{j+2}
+            tc_fence_after();
             issue_qk(0, sb, st(ki));
             umma_commit(&s_full[sb]);
             umma_commit(&kv_empty[st(ki)]);
           }
-          __syncwarp();
         }
       }
+      umma_commit(o_final);
     }
-    if (lane == 0) umma_commit(o_final);
     __syncwarp();
   } else if (warp >= 4 && (two || warp < 8)) {
     // ===================== softmax warpgroups =====================
@@ -320,7 +327,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const float m_used = need ? m_new : m_run;
       const float alpha = need ? fast_exp2((m_run - m_new) * sl2) : 1.0f;
       if (j > 0 && __any_sync(0xffffffffu, need)) {
-        // rescale this row's O accumulator in TMEM
+        // rescale this row's O accumulator in TMEM.  Two-tile mode: s_full(j) was committed after
+        // P.V(j-1) in issue order, so O is quiescent.  Single-tile mode: Q.K^T(j) is issued BEFORE
+        // P.V(j-1) (other S buffer), so wait for that P.V's own commit (phases j-1 or j complete).
+        if (!two) {
+          mbar_wait(o_done, static_cast<uint32_t>((j - 1) & 1));
+          tc_fence_after();
+        }
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t o[32];
@@ -336,53 +349,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       // a row whose every visible key so far is masked (local window) keeps m = -inf: use 0
       const float nms = (m_used == -INFINITY) ? 0.f : -m_used * sl2;
       float rowsum = 0.f;
-      uint32_t pk[64];
-      if constexpr (kPHalf) {
-        // P in fp16: the exponent argument is formed in fp32 (a = s*c - m), rounded to f16x2 and
-        // exponentiated two-at-a-time on the MUFU (ex2.approx.ftz.f16x2): half the MUFU work and
-        // no pack instructions; |a| <= 16 where it matters, so the f16 argument error (<= 2^-8)
-        // is below the 2^-9 relative rounding of a bf16 P.  Row sums: short f16x2 trees -> fp32.
+      // exponentiate one 32-key quarter of the row into 16 packed columns
+      auto quarter_exp = [&](const uint32_t (&r)[32], uint32_t* pk) {
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-          pk[c] = ex2_f16x2(fmaf(__uint_as_float(r0[2 * c]), sl2, nms), fmaf(__uint_as_float(r0[2 * c + 1]), sl2, nms));
-          pk[16 + c] = ex2_f16x2(fmaf(__uint_as_float(r1[2 * c]), sl2, nms), fmaf(__uint_as_float(r1[2 * c + 1]), sl2, nms));
-          pk[32 + c] = ex2_f16x2(fmaf(__uint_as_float(r2[2 * c]), sl2, nms), fmaf(__uint_as_float(r2[2 * c + 1]), sl2, nms));
-          pk[48 + c] = ex2_f16x2(fmaf(__uint_as_float(r3[2 * c]), sl2, nms), fmaf(__uint_as_float(r3[2 * c + 1]), sl2, nms));
+          const float a0 = fast_exp2(fmaf(__uint_as_float(r[2 * c]), sl2, nms));
+          const float a1 = fast_exp2(fmaf(__uint_as_float(r[2 * c + 1]), sl2, nms));
+          rowsum += a0 + a1;
+          pk[c] = kBf16 ? pack_bf16x2(a0, a1) : pack_f16x2(a0, a1);
         }
-#pragma unroll
-        for (int c = 0; c < 64; c += 4) {
-          const __half2 s4 = __hadd2(__hadd2(*reinterpret_cast<__half2*>(&pk[c]), *reinterpret_cast<__half2*>(&pk[c + 1])),
-                                     __hadd2(*reinterpret_cast<__half2*>(&pk[c + 2]), *reinterpret_cast<__half2*>(&pk[c + 3])));
-          const float2 f = __half22float2(s4);
-          rowsum += f.x + f.y;
-        }
+      };
+      // tcgen05.wait::st is warp-wide (.sync.aligned): once it returns every lane's slice of P is in
+      // TMEM, so one elected arrive per warp publishes it
+      auto hand_over = [&](int part) {
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[sb * kParts + part]);
+      };
+      if constexpr (kParts == 4) {
+        uint32_t pk[16];
+        quarter_exp(r0, pk); tmem_st_x16(tS + 0, pk); hand_over(0);
+        quarter_exp(r1, pk); tmem_st_x16(tS + 16, pk); hand_over(1);
+        quarter_exp(r2, pk); tmem_st_x16(tS + 32, pk); hand_over(2);
+        quarter_exp(r3, pk); tmem_st_x16(tS + 48, pk); hand_over(3);
       } else {
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        float a0 = fast_exp2(fmaf(__uint_as_float(r0[2 * c]), sl2, nms));
-        float a1 = fast_exp2(fmaf(__uint_as_float(r0[2 * c + 1]), sl2, nms));
-        float b0 = fast_exp2(fmaf(__uint_as_float(r1[2 * c]), sl2, nms));
-        float b1 = fast_exp2(fmaf(__uint_as_float(r1[2 * c + 1]), sl2, nms));
-        float c0 = fast_exp2(fmaf(__uint_as_float(r2[2 * c]), sl2, nms));
-        float c1 = fast_exp2(fmaf(__uint_as_float(r2[2 * c + 1]), sl2, nms));
-        // the last quarter of the tile goes through the polynomial (FMA pipe) instead of the MUFU
-        float d0 = kPolyExp ? poly_exp2(fmaf(__uint_as_float(r3[2 * c]), sl2, nms))
-                            : fast_exp2(fmaf(__uint_as_float(r3[2 * c]), sl2, nms));
-        float d1 = kPolyExp ? poly_exp2(fmaf(__uint_as_float(r3[2 * c + 1]), sl2, nms))
-                            : fast_exp2(fmaf(__uint_as_float(r3[2 * c + 1]), sl2, nms));
-        rowsum += (a0 + a1) + (b0 + b1) + (c0 + c1) + (d0 + d1);
-        pk[c] = kBf16 ? pack_bf16x2(a0, a1) : pack_f16x2(a0, a1);
-        pk[16 + c] = kBf16 ? pack_bf16x2(b0, b1) : pack_f16x2(b0, b1);
-        pk[32 + c] = kBf16 ? pack_bf16x2(c0, c1) : pack_f16x2(c0, c1);
-        pk[48 + c] = kBf16 ? pack_bf16x2(d0, d1) : pack_f16x2(d0, d1);
-      }
+        uint32_t pk[32];
+        quarter_exp(r0, pk);
+        quarter_exp(r1, pk + 16);
+        tmem_st_x32(tS + 0, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
+        if constexpr (kParts == 2) hand_over(0);
+        quarter_exp(r2, pk);
+        quarter_exp(r3, pk + 16);
+        tmem_st_x32(tS + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
+        hand_over(kParts - 1);
       }
       l_run += rowsum;
-      tmem_st_x32(tS + 0, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
-      tmem_st_x32(tS + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_ready[sb]);
     }
 
     // ---- epilogue: O / l -> global ----
@@ -455,28 +457,22 @@ int attn_fwd(int dtype, const void* q, int ldq, const void* k, int ldk, const vo
   if (rc != KR_OK) return rc;
   rc = make_tmap_2d(&tv, v, p.Lkv, static_cast<uint64_t>(p.heads) * kHeadDim, ldv, kTileKV, 64, bf);
   if (rc != KR_OK) return rc;
-  // KR_ATTN_P_F16=1 selects the experimental fp16-P softmax (exp on f16x2) instead of the default
-  // bf16-P one (fp32 exp per element, P rounded to the KV dtype like FlashAttention-2)
-  static const bool p_f16 = [] { const char* e = getenv("KR_ATTN_P_F16"); return e != nullptr && e[0] == '1'; }();
-  // KR_ATTN_POLY=1 moves a quarter of the exponentials to an FMA-pipe polynomial (FlashAttention-4 style).
-  // Measured on B200 (r01): 966 TF/s with it vs 1100 TF/s without at Lq 4680 / Lkv 9360 — the softmax
-  // warps are issue-bound, not MUFU-bound, so it stays off by default.
-  static const bool poly = [] { const char* e = getenv("KR_ATTN_POLY"); return e != nullptr && e[0] == '1'; }();
-  auto kern = bf ? (p_f16 ? attn_fwd_kernel<true, true, false>
-                          : (poly ? attn_fwd_kernel<true, false, true> : attn_fwd_kernel<true, false, false>))
-                 : (poly ? attn_fwd_kernel<false, false, true> : attn_fwd_kernel<false, false, false>);
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[bf ? 0 : 1]) {   // (p_f16 is process-constant, so one flag per dtype suffices)
-    cudaError_t e =
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
-    if (e != cudaSuccess) {
-      set_last_error("attn_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-      return KR_ERR_CUDA;
+  using Kern = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams);
+  Kern kern = bf ? attn_fwd_kernel<true> : attn_fwd_kernel<false>;
+  {
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[bf ? 0 : 1]) {
+      cudaError_t e =
+          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+      if (e != cudaSuccess) {
+        set_last_error("attn_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        return KR_ERR_CUDA;
+      }
+      attr_set[bf ? 0 : 1] = true;
     }
-    attr_set[bf ? 0 : 1] = true;
+    dim3 grid(((p.Lq + 2 * kTileQ - 1) / (2 * kTileQ)) * p.heads);
+    kern<<<grid, kAttnThreads, kAttnSmem, stream>>>(tq, tk, tv, p);
   }
-  dim3 grid(((p.Lq + 2 * kTileQ - 1) / (2 * kTileQ)) * p.heads);
-  kern<<<grid, kAttnThreads, kAttnSmem, stream>>>(tq, tk, tv, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_last_error("attn_fwd: launch failed: %s", cudaGetErrorString(e));

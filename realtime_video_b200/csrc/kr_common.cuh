@@ -289,26 +289,6 @@ KR_DEVICE float2 unpack_f16x2(uint32_t u) {
   __half2 v = *reinterpret_cast<__half2*>(&u);
   return __half22float2(v);
 }
-// 2^lo, 2^hi as packed f16x2 (lo in the low half): one cvt.pack + one MUFU op for two values
-KR_DEVICE uint32_t ex2_f16x2(float lo, float hi) {
-  uint32_t h, y;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(h));
-  return y;
-}
-// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], cubic
-// minimax of 2^f (max relative error 2.0e-4, far below the 2^-9 rounding of a bf16 probability),
-// exponent added through the integer bits.  Used for a fraction of the attention exponentials so the
-// 16-per-clock MUFU stops being the co-limiter of the tensor pipe.
-KR_DEVICE float poly_exp2(float x) {
-  x = fmaxf(x, -125.0f);
-  const float t = x + 12582912.0f;                 // 1.5 * 2^23: integer part lands in the mantissa
-  const float f = x - (t - 12582912.0f);
-  float p = fmaf(f, 0.05302752f, 0.24221395f);     // near-minimax cubic, max rel. error 2.0e-4
-  p = fmaf(p, f, 0.69357258f);
-  p = fmaf(p, f, 0.99995905f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
 KR_DEVICE float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

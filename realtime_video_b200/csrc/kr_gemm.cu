@@ -93,7 +93,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -117,7 +117,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================== MMA issuer: ONE thread runs the whole loop =====================
     // (a warp-wide wait + elect + __syncwarp per k-block left the tensor pipe idle ~25 % of the time:
     //  the issue loop, not operand delivery, was the limiter — profiles/r01_ncu_gemm_ffn1.txt)
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc<kBf16>(BLOCK_M, BLOCK_N, 0, 0);
       const uint64_t desc_hi = make_smem_desc(0, 16, 1024) & 0xFFFFFFFF00000000ull;
       const uint32_t desc_lo_c = static_cast<uint32_t>(make_smem_desc(0, 16, 1024));

@@ -228,7 +228,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -255,7 +255,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only, ONE thread runs the whole loop) =====================
-    if (leader && lane == 0) {
+    if (leader && elect_one()) {
       constexpr uint32_t idesc = make_idesc<kBf16>(2 * G2_BLOCK_M, G2_BLOCK_N, 0, 0);
       // descriptor = constant high word | (start address >> 4); K-major SW128: LBO 16 B, SBO 1024 B
       const uint64_t desc_hi = make_smem_desc(0, 16, 1024) & 0xFFFFFFFF00000000ull;

@@ -132,7 +132,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in64, const __grid_cons
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -172,7 +172,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in64, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: ONE thread runs the whole loop =====================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc<kBf16>(128, Cfg::kMmaN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;

@@ -234,8 +234,22 @@ def t_perf():
     print(f"PERF ln_modulate: {ms:.3f} ms {2 * x.numel() * 2 / ms / 1e6:.0f} GB/s", flush=True)
 
 
+def t_attnperf():
+    torch.manual_seed(3)
+    L, D, H = 4680, 5120, 40
+    q = torch.randn(L, D, device=dev, dtype=torch.bfloat16)
+    import os
+    tag = f"parts={os.environ.get('KR_ATTN_PARTS', 'default')} packed={os.environ.get('KR_ATTN_PACKED', 'default')}"
+    for Lkv in (9360, 4680, 512):
+        k = torch.randn(Lkv, D, device=dev, dtype=torch.bfloat16)
+        v = torch.randn(Lkv, D, device=dev, dtype=torch.bfloat16)
+        o = torch.empty(L, D, device=dev, dtype=torch.bfloat16)
+        ms = timeit(lambda: ops.attention(q, k, v, heads=H, out=o), n=30, warm=5)
+        print(f"PERF attn [{tag}] Lq={L} Lkv={Lkv}: {ms:.3f} ms {4.0 * L * Lkv * D / ms / 1e9:.1f} TF/s", flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1]
     t0 = time.time()
-    {"gemm": t_gemm, "attn": t_attn, "elem": t_elem, "perf": t_perf}[which]()
+    {"gemm": t_gemm, "attn": t_attn, "elem": t_elem, "perf": t_perf, "attnperf": t_attnperf}[which]()
     print(f"[{which}] done in {time.time() - t0:.1f}s", flush=True)
