@@ -19,6 +19,8 @@
 #include "kr_common.cuh"
 #include "kr_ops.h"
 
+#include <cstdlib>
+
 namespace kr {
 
 static constexpr int kConvThreads = 192;
@@ -74,6 +76,157 @@ KR_DEVICE float load16(const uint16_t* p) {
   uint16_t u = *p;
   return kBf16 ? __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&u))
                : __half2float(*reinterpret_cast<__half*>(&u));
+}
+
+// Epilogue of one output pixel (thread = TMEM lane): bias, optional residual, rounding, raw store, fused
+// RMS_norm*sqrt(C)*gamma -> SiLU store, or clamp -> fp32 NCHW pixels (N == 16 head).  `t_row` is the TMEM
+// address of this thread's accumulator row; the accumulator is released on `empty_bar` (one arrive per warp)
+// as soon as its last column has been read.
+template <int N, bool kBf16>
+KR_DEVICE void conv_epilogue_pixel(const ConvParams& p, uint32_t t_row, int t, int h, int w, uint64_t* empty_bar,
+                                   int lane) {
+  const uint16_t* bias = reinterpret_cast<const uint16_t*>(p.bias);
+  const uint16_t* gamma = reinterpret_cast<const uint16_t*>(p.gamma);
+  // sub2: stride-2 convolution with right/bottom zero pad (ZeroPad2d((0,1,0,1)) + Conv2d(stride 2),
+  // vae.py:84-92) evaluated as the stride-1 conv at the odd positions: out(i,j) = full(2i+1, 2j+1)
+  const bool ok = h < p.H && w < p.W && (p.sub2 == 0 || ((h & 1) && (w & 1)));
+  const long pix = p.sub2 ? static_cast<long>(h >> 1) * (p.W >> 1) + (w >> 1)
+                          : static_cast<long>(h) * p.W + w;
+
+  if constexpr (N == 16) {
+    // head conv: bias, round, clamp, fp32 NCHW pixels
+    uint32_t v[16];
+    tmem_ld_x16(t_row, v);
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar);
+    if (ok) {
+      for (int c = 0; c < p.cout; ++c) {
+        float x = __uint_as_float(v[c]) + (bias ? load16<kBf16>(bias + c) : 0.f);
+        x = rnd16<kBf16>(x);
+        if (p.out_pix != nullptr) {
+          x = fminf(fmaxf(x, -1.f), 1.f);
+          p.out_pix[(static_cast<long>(t) * p.cout + c) * p.H * p.W + pix] = x;
+        }
+      }
+    }
+  } else {
+    const uint16_t* res = p.residual
+        ? reinterpret_cast<const uint16_t*>(p.residual) + t * p.res_frame + pix * p.res_pix : nullptr;
+    uint16_t* oraw = p.out_raw
+        ? reinterpret_cast<uint16_t*>(p.out_raw) + t * p.raw_frame + pix * p.raw_pix : nullptr;
+    uint16_t* onrm = p.out_norm
+        ? reinterpret_cast<uint16_t*>(p.out_norm) + t * p.norm_frame + pix * p.norm_pix : nullptr;
+    float sumsq = 0.f;
+    // ---- pass 1: bias (+ residual), round, raw store, sum of squares; keep v in TMEM ----
+#pragma unroll 1
+    for (int c = 0; c < N / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_x32(t_row + c * 32, v);
+      tmem_ld_wait();
+      if (c == N / 32 - 1 && p.out_norm == nullptr) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar);
+      }
+      float f[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+      if (bias != nullptr) {
+        const uint4* b4 = reinterpret_cast<const uint4*>(bias + c * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 bb = __ldg(b4 + q);
+          const uint32_t wv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+          for (int hh = 0; hh < 4; ++hh) {
+            const float2 g = unpack16<kBf16>(wv[hh]);
+            f[q * 8 + hh * 2] += g.x;
+            f[q * 8 + hh * 2 + 1] += g.y;
+          }
+        }
+      }
+      if (res != nullptr && ok) {
+        // reference: y = conv(...) (rounded to 16-bit), out = x + y (rounded)
+        const uint4* r4 = reinterpret_cast<const uint4*>(res + c * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 rr = r4[q];
+          const uint32_t wv[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+          for (int hh = 0; hh < 4; ++hh) {
+            const float2 g = unpack16<kBf16>(wv[hh]);
+            f[q * 8 + hh * 2] = g.x + rnd16<kBf16>(f[q * 8 + hh * 2]);
+            f[q * 8 + hh * 2 + 1] = g.y + rnd16<kBf16>(f[q * 8 + hh * 2 + 1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        f[i] = rnd16<kBf16>(f[i]);
+        sumsq += f[i] * f[i];
+      }
+      if (oraw != nullptr && ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack16<kBf16>(f[q * 8 + 0], f[q * 8 + 1]);
+          o.y = pack16<kBf16>(f[q * 8 + 2], f[q * 8 + 3]);
+          o.z = pack16<kBf16>(f[q * 8 + 4], f[q * 8 + 5]);
+          o.w = pack16<kBf16>(f[q * 8 + 6], f[q * 8 + 7]);
+          reinterpret_cast<uint4*>(oraw + c * 32)[q] = o;
+        }
+      }
+      if (p.out_norm != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(f[i]);
+        tmem_st_x32(t_row + c * 32, v);
+      }
+    }
+    // ---- pass 2: F.normalize(x, dim=C) * sqrt(C) * gamma -> SiLU ----
+    if (p.out_norm != nullptr) {
+      tmem_st_wait();
+      const float nrm = rnd16<kBf16>(sqrtf(sumsq));
+      const float inv = 1.0f / fmaxf(nrm, 1e-30f);
+#pragma unroll 1
+      for (int c = 0; c < N / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(t_row + c * 32, v);
+        tmem_ld_wait();
+        if (c == N / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty_bar);
+        }
+        if (ok) {
+          const uint4* g4 = reinterpret_cast<const uint4*>(gamma + c * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 gg = __ldg(g4 + q);
+            const uint32_t wv[4] = {gg.x, gg.y, gg.z, gg.w};
+            float o[8];
+#pragma unroll
+            for (int hh = 0; hh < 4; ++hh) {
+              const float2 g = unpack16<kBf16>(wv[hh]);
+              float a = rnd16<kBf16>(__uint_as_float(v[q * 8 + hh * 2]) * inv);
+              float b = rnd16<kBf16>(__uint_as_float(v[q * 8 + hh * 2 + 1]) * inv);
+              a = rnd16<kBf16>(rnd16<kBf16>(a * p.norm_scale) * g.x);
+              b = rnd16<kBf16>(rnd16<kBf16>(b * p.norm_scale) * g.y);
+              o[hh * 2] = a / (1.0f + __expf(-a));
+              o[hh * 2 + 1] = b / (1.0f + __expf(-b));
+            }
+            uint4 ov;
+            ov.x = pack16<kBf16>(o[0], o[1]);
+            ov.y = pack16<kBf16>(o[2], o[3]);
+            ov.z = pack16<kBf16>(o[4], o[5]);
+            ov.w = pack16<kBf16>(o[6], o[7]);
+            reinterpret_cast<uint4*>(onrm + c * 32)[q] = ov;
+          }
+        }
+      }
+    }
+  }
 }
 
 template <int CIN, int N, bool kBf16>
@@ -230,156 +383,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in64, const __grid_cons
     const int r = quarter * 32 + lane;          // row in tile
     int acc = 0;
     uint32_t acc_phase = 0;
-    const uint16_t* bias = reinterpret_cast<const uint16_t*>(p.bias);
-    const uint16_t* gamma = reinterpret_cast<const uint16_t*>(p.gamma);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int t = tile / tiles_per_frame;
       const int rem = tile % tiles_per_frame;
       const int h = (rem / tiles_w) * p.TH + r / p.TW;
       const int w = (rem % tiles_w) * p.TW + r % p.TW;
-      // sub2: stride-2 convolution with right/bottom zero pad (ZeroPad2d((0,1,0,1)) + Conv2d(stride 2),
-      // vae.py:84-92) evaluated as the stride-1 conv at the odd positions: out(i,j) = full(2i+1, 2j+1)
-      const bool ok = h < p.H && w < p.W && (p.sub2 == 0 || ((h & 1) && (w & 1)));
-      const long pix = p.sub2 ? static_cast<long>(h >> 1) * (p.W >> 1) + (w >> 1)
-                              : static_cast<long>(h) * p.W + w;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * Cfg::kAccStride;
-
-      if constexpr (N == 16) {
-        // head conv: bias, round, clamp, fp32 NCHW pixels
-        uint32_t v[16];
-        tmem_ld_x16(t_row, v);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        if (ok) {
-          for (int c = 0; c < p.cout; ++c) {
-            float x = __uint_as_float(v[c]) + (bias ? load16<kBf16>(bias + c) : 0.f);
-            x = rnd16<kBf16>(x);
-            if (p.out_pix != nullptr) {
-              x = fminf(fmaxf(x, -1.f), 1.f);
-              p.out_pix[(static_cast<long>(t) * p.cout + c) * p.H * p.W + pix] = x;
-            }
-          }
-        }
-      } else {
-        const uint16_t* res = p.residual
-            ? reinterpret_cast<const uint16_t*>(p.residual) + t * p.res_frame + pix * p.res_pix : nullptr;
-        uint16_t* oraw = p.out_raw
-            ? reinterpret_cast<uint16_t*>(p.out_raw) + t * p.raw_frame + pix * p.raw_pix : nullptr;
-        uint16_t* onrm = p.out_norm
-            ? reinterpret_cast<uint16_t*>(p.out_norm) + t * p.norm_frame + pix * p.norm_pix : nullptr;
-        float sumsq = 0.f;
-        // ---- pass 1: bias (+ residual), round, raw store, sum of squares; keep v in TMEM ----
-#pragma unroll 1
-        for (int c = 0; c < N / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_x32(t_row + c * 32, v);
-          tmem_ld_wait();
-          if (c == N / 32 - 1 && p.out_norm == nullptr) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-          }
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          if (bias != nullptr) {
-            const uint4* b4 = reinterpret_cast<const uint4*>(bias + c * 32);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 bb = __ldg(b4 + q);
-              const uint32_t wv[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-              for (int hh = 0; hh < 4; ++hh) {
-                const float2 g = unpack16<kBf16>(wv[hh]);
-                f[q * 8 + hh * 2] += g.x;
-                f[q * 8 + hh * 2 + 1] += g.y;
-              }
-            }
-          }
-          if (res != nullptr && ok) {
-            // reference: y = conv(...) (rounded to 16-bit), out = x + y (rounded)
-            const uint4* r4 = reinterpret_cast<const uint4*>(res + c * 32);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 rr = r4[q];
-              const uint32_t wv[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-              for (int hh = 0; hh < 4; ++hh) {
-                const float2 g = unpack16<kBf16>(wv[hh]);
-                f[q * 8 + hh * 2] = g.x + rnd16<kBf16>(f[q * 8 + hh * 2]);
-                f[q * 8 + hh * 2 + 1] = g.y + rnd16<kBf16>(f[q * 8 + hh * 2 + 1]);
-              }
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            f[i] = rnd16<kBf16>(f[i]);
-            sumsq += f[i] * f[i];
-          }
-          if (oraw != nullptr && ok) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 o;
-              o.x = pack16<kBf16>(f[q * 8 + 0], f[q * 8 + 1]);
-              o.y = pack16<kBf16>(f[q * 8 + 2], f[q * 8 + 3]);
-              o.z = pack16<kBf16>(f[q * 8 + 4], f[q * 8 + 5]);
-              o.w = pack16<kBf16>(f[q * 8 + 6], f[q * 8 + 7]);
-              reinterpret_cast<uint4*>(oraw + c * 32)[q] = o;
-            }
-          }
-          if (p.out_norm != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(f[i]);
-            tmem_st_x32(t_row + c * 32, v);
-          }
-        }
-        // ---- pass 2: F.normalize(x, dim=C) * sqrt(C) * gamma -> SiLU ----
-        if (p.out_norm != nullptr) {
-          tmem_st_wait();
-          const float nrm = rnd16<kBf16>(sqrtf(sumsq));
-          const float inv = 1.0f / fmaxf(nrm, 1e-30f);
-#pragma unroll 1
-          for (int c = 0; c < N / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld_x32(t_row + c * 32, v);
-            tmem_ld_wait();
-            if (c == N / 32 - 1) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-            }
-            if (ok) {
-              const uint4* g4 = reinterpret_cast<const uint4*>(gamma + c * 32);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 gg = __ldg(g4 + q);
-                const uint32_t wv[4] = {gg.x, gg.y, gg.z, gg.w};
-                float o[8];
-#pragma unroll
-                for (int hh = 0; hh < 4; ++hh) {
-                  const float2 g = unpack16<kBf16>(wv[hh]);
-                  float a = rnd16<kBf16>(__uint_as_float(v[q * 8 + hh * 2]) * inv);
-                  float b = rnd16<kBf16>(__uint_as_float(v[q * 8 + hh * 2 + 1]) * inv);
-                  a = rnd16<kBf16>(rnd16<kBf16>(a * p.norm_scale) * g.x);
-                  b = rnd16<kBf16>(rnd16<kBf16>(b * p.norm_scale) * g.y);
-                  o[hh * 2] = a / (1.0f + __expf(-a));
-                  o[hh * 2 + 1] = b / (1.0f + __expf(-b));
-                }
-                uint4 ov;
-                ov.x = pack16<kBf16>(o[0], o[1]);
-                ov.y = pack16<kBf16>(o[2], o[3]);
-                ov.z = pack16<kBf16>(o[4], o[5]);
-                ov.w = pack16<kBf16>(o[6], o[7]);
-                reinterpret_cast<uint4*>(onrm + c * 32)[q] = ov;
-              }
-            }
-          }
-        }
-      }
+      conv_epilogue_pixel<N, kBf16>(p, t_row, t, h, w, &tmem_empty[acc], lane);
       if (++acc == Cfg::kNumAcc) {
         acc = 0;
         acc_phase ^= 1;
@@ -393,6 +405,262 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_in64, const __grid_cons
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv_halo_kernel: the 3x3-spatial convs of the wide stages (N = 96 / 192 output channels).
+//
+// conv_igemm_kernel fetches a fresh 128-pixel input tile AND a fresh weight tile for every one of the
+// kt*9 taps: ncu on the 96->96 stage-3 conv shows 44 GB of L2->SM traffic for 1.3 GB of input (12.9 TB/s,
+// the chip's L2->SM ceiling) and the tensor pipe at 34 %.  Here
+//   * one work item = 256 output pixels of one frame: two 16(h) x 8(w) MMA tiles side by side;
+//   * per (kt, 64-channel chunk) ONE halo box {64 ch, 24 w, 18 h} (18 x 24 = 432 rows of 128 B, pitch 24
+//     rows) is loaded, and the 9 spatial taps are MMAs over SHIFTED WINDOWS of it: the A descriptor of
+//     tap (kh, kw), tile u starts (kh*24 + 8u + kw) rows into the box with SBO = 24 rows.  The tensor core
+//     derives the 128-byte swizzle from absolute shared-memory address bits, so a start address that is
+//     not 1024-byte aligned needs no "base offset" (verified on B200: tools/experiments/umma_shift_test.cu,
+//     profiles/r01_umma_shifted_window_test.log);
+//   * every weight tile {64 k, N} is used by both pixel tiles (two accumulators in TMEM).
+// Input traffic per pixel drops 9x * (128/216) and weight traffic 2x.  Borders are the TMA out-of-bounds
+// zero fill as before; a partial last channel chunk (CIN = 96) is loaded 64 wide (zero filled) and only
+// its valid k-steps are issued.
+template <int CIN, int N>
+struct HaloCfg {
+  static constexpr int kChunks = (CIN + 63) / 64;
+  static constexpr int kLastK = (CIN % 64 == 0) ? 4 : (CIN % 64) / 16;   // k-steps of the last chunk
+  static constexpr int kBoxW = 24, kBoxH = 18;
+  static constexpr int kABytes = kBoxW * kBoxH * 128;             // 55296 = 54 KB
+  static constexpr int kAStages = 2;
+  static constexpr int kBBytes = N * 128;
+  static constexpr int kBStages = (96 * 1024) / kBBytes > 8 ? 8 : (96 * 1024) / kBBytes;
+  static constexpr int kAccSets = (4 * N <= 512) ? 2 : 1;        // double-buffer the accumulators if they fit
+  static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + 1024 + 512;
+  static_assert(kABytes % 1024 == 0 && kBBytes % 1024 == 0, "swizzle alignment");
+  static_assert(2 * N * kAccSets <= 512, "TMEM columns");
+};
+static constexpr int kHaloThreads = 64 + 256;   // TMA warp, MMA warp, 2 x 4 epilogue warps
+
+template <int CIN, int N, bool kBf16>
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w,
+                 const ConvParams p) {
+  using Cfg = HaloCfg<CIN, N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kAStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + Cfg::kBStages * Cfg::kBBytes);
+  uint64_t* a_full = bars;                         // [kAStages]
+  uint64_t* a_empty = a_full + Cfg::kAStages;      // [kAStages]
+  uint64_t* b_full = a_empty + Cfg::kAStages;      // [kBStages]
+  uint64_t* b_empty = b_full + Cfg::kBStages;      // [kBStages]
+  uint64_t* tmem_full = b_empty + Cfg::kBStages;   // [4] accumulator = set * 2 + tile
+  uint64_t* tmem_empty = tmem_full + 4;            // [4]
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int items_w = (p.W + 15) / 16;
+  const int items_h = (p.H + 15) / 16;
+  const int items_per_frame = items_w * items_h;
+  const int num_items = p.T * items_per_frame;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_in);
+    prefetch_tmap(&tm_w);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < Cfg::kAStages; ++i) {
+        mbar_init(&a_full[i], 1);
+        mbar_init(&a_empty[i], 1);
+      }
+      for (int i = 0; i < Cfg::kBStages; ++i) {
+        mbar_init(&b_full[i], 1);
+        mbar_init(&b_empty[i], 1);
+      }
+      for (int i = 0; i < 4; ++i) {
+        mbar_init(&tmem_full[i], 1);
+        mbar_init(&tmem_empty[i], 4);   // one arrive per epilogue warp of the tile
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_base_smem);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int t = item / items_per_frame;
+        const int rem = item % items_per_frame;
+        const int h0 = (rem / items_w) * 16;
+        const int w0 = (rem % items_w) * 16;
+        for (int kt = 0; kt < p.KT; ++kt) {
+          for (int c = 0; c < Cfg::kChunks; ++c) {
+            mbar_wait(&a_empty[sa], pa ^ 1);
+            mbar_expect_tx(&a_full[sa], Cfg::kABytes);
+            tma_load_4d(smem_a + sa * Cfg::kABytes, &tm_in, &a_full[sa], c * 64, w0 - 1, h0 - 1, t + kt);
+            if (++sa == Cfg::kAStages) {
+              sa = 0;
+              pa ^= 1;
+            }
+            for (int sp = 0; sp < 9; ++sp) {
+              mbar_wait(&b_empty[sb], pb ^ 1);
+              mbar_expect_tx(&b_full[sb], Cfg::kBBytes);
+              tma_load_2d(smem_b + sb * Cfg::kBBytes, &tm_w, &b_full[sb], (kt * 9 + sp) * CIN + c * 64, 0);
+              if (++sb == Cfg::kBStages) {
+                sb = 0;
+                pb ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc<kBf16>(128, N, 0, 0);
+      const uint64_t a_hi = make_smem_desc(0, 16, Cfg::kBoxW * 128) & 0xFFFFFFFF00000000ull;
+      const uint32_t a_lo_c = static_cast<uint32_t>(make_smem_desc(0, 16, Cfg::kBoxW * 128));
+      const uint64_t b_hi = make_smem_desc(0, 16, 1024) & 0xFFFFFFFF00000000ull;
+      const uint32_t b_lo_c = static_cast<uint32_t>(make_smem_desc(0, 16, 1024));
+      const uint32_t a0 = smem_u32(smem_a), b0 = smem_u32(smem_b);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int set = 0;
+      uint32_t set_phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        mbar_wait(&tmem_empty[set * 2 + 0], set_phase ^ 1);
+        mbar_wait(&tmem_empty[set * 2 + 1], set_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + set * 2 * N;
+        bool first = true;
+        for (int kt = 0; kt < p.KT; ++kt) {
+          for (int c = 0; c < Cfg::kChunks; ++c) {
+            const int ksteps = (c == Cfg::kChunks - 1) ? Cfg::kLastK : 4;
+            mbar_wait(&a_full[sa], pa);
+            tc_fence_after();
+            const uint32_t a_st = a0 + sa * Cfg::kABytes;
+#pragma unroll 1
+            for (int sp = 0; sp < 9; ++sp) {
+              const int kh = sp / 3, kw = sp - kh * 3;
+              mbar_wait(&b_full[sb], pb);
+              tc_fence_after();
+              const uint32_t b_st = b0 + sb * Cfg::kBBytes;
+              const uint32_t a_win = a_st + (kh * Cfg::kBoxW + kw) * 128;
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (k < ksteps) {
+                    const uint64_t ad = a_hi | (a_lo_c + ((a_win + u * 8 * 128 + k * 32) >> 4));
+                    const uint64_t bd = b_hi | (b_lo_c + ((b_st + k * 32) >> 4));
+                    umma_ss(d_tmem + u * N, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
+                  }
+                }
+              }
+              first = false;
+              umma_commit(&b_empty[sb]);
+              if (++sb == Cfg::kBStages) {
+                sb = 0;
+                pb ^= 1;
+              }
+            }
+            umma_commit(&a_empty[sa]);
+            if (++sa == Cfg::kAStages) {
+              sa = 0;
+              pa ^= 1;
+            }
+          }
+        }
+        umma_commit(&tmem_full[set * 2 + 0]);
+        umma_commit(&tmem_full[set * 2 + 1]);
+        if (++set == Cfg::kAccSets) {
+          set = 0;
+          set_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: warps 2..5 -> tile 0, warps 6..9 -> tile 1 =====================
+    const int u = (warp - 2) >> 2;
+    const int quarter = warp & 3;               // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;          // pixel row of the 16 x 8 tile
+    int set = 0;
+    uint32_t set_phase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int t = item / items_per_frame;
+      const int rem = item % items_per_frame;
+      const int h = (rem / items_w) * 16 + (r >> 3);
+      const int w = (rem % items_w) * 16 + u * 8 + (r & 7);
+      const int acc = set * 2 + u;
+      mbar_wait(&tmem_full[acc], set_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * N;
+      conv_epilogue_pixel<N, kBf16>(p, t_row, t, h, w, &tmem_empty[acc], lane);
+      if (++set == Cfg::kAccSets) {
+        set = 0;
+        set_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int CIN, int N, bool kBf16>
+static int launch_conv_halo(const void* in, int t_in, const void* wgt, int w_rows, const ConvParams& p,
+                            cudaStream_t stream) {
+  using Cfg = HaloCfg<CIN, N>;
+  CUtensorMap tin, tw;
+  const uint64_t idims[4] = {static_cast<uint64_t>(CIN), static_cast<uint64_t>(p.W),
+                             static_cast<uint64_t>(p.H), static_cast<uint64_t>(t_in)};
+  const uint64_t istr[3] = {static_cast<uint64_t>(CIN) * 2, static_cast<uint64_t>(p.W) * CIN * 2,
+                            static_cast<uint64_t>(p.H) * p.W * CIN * 2};
+  const uint32_t ibox[4] = {64, Cfg::kBoxW, Cfg::kBoxH, 1};
+  int rc = make_tmap_nd(&tin, in, 4, idims, istr, ibox, kBf16, 128);
+  if (rc != KR_OK) return rc;
+  const int taps = p.KT * 9;
+  const uint64_t wdims[2] = {static_cast<uint64_t>(taps) * CIN, static_cast<uint64_t>(w_rows)};
+  const uint64_t wstr[1] = {static_cast<uint64_t>(taps) * CIN * 2};
+  const uint32_t wbox[2] = {64, static_cast<uint32_t>(N)};
+  rc = make_tmap_nd(&tw, wgt, 2, wdims, wstr, wbox, kBf16, 128);
+  if (rc != KR_OK) return rc;
+  auto kern = conv_halo_kernel<CIN, N, kBf16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_last_error("vae_conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return KR_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int num_items = p.T * ((p.W + 15) / 16) * ((p.H + 15) / 16);
+  int grid = sm_count();
+  if (grid > num_items) grid = num_items;
+  kern<<<grid, kHaloThreads, Cfg::kSmemBytes, stream>>>(tin, tw, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("vae_conv: launch failed: %s", cudaGetErrorString(e));
+    return KR_ERR_CUDA;
+  }
+  return KR_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -452,6 +720,18 @@ static int launch_conv(const void* in, int t_in, const void* wgt, int w_rows, co
 template <bool kBf16>
 static int dispatch_conv(int cin, int n, const void* in, int t_in, const void* wgt, int w_rows,
                          const ConvParams& p, cudaStream_t s) {
+  // 3x3 spatial taps with 96 / 192 output channels: halo-reuse kernel (KR_CONV_HALO=0 -> per-tap kernel)
+  static const bool halo = [] { const char* e = getenv("KR_CONV_HALO"); return e == nullptr || e[0] != '0'; }();
+  if (halo && p.KH == 3 && p.KW == 3 && (p.KT == 1 || p.KT == 3) && w_rows >= n) {
+#define KR_HALO_CASE(CI, NN) \
+    if (cin == CI && n == NN) return launch_conv_halo<CI, NN, kBf16>(in, t_in, wgt, w_rows, p, s);
+    KR_HALO_CASE(384, 192)
+    KR_HALO_CASE(192, 192)
+    KR_HALO_CASE(192, 96)
+    KR_HALO_CASE(96, 96)
+    KR_HALO_CASE(96, 192)
+#undef KR_HALO_CASE
+  }
 #define KR_CONV_CASE(CI, NN) \
   if (cin == CI && n == NN) return launch_conv<CI, NN, kBf16>(in, t_in, wgt, w_rows, p, s);
   KR_CONV_CASE(64, 384)

@@ -5,7 +5,7 @@ import time
 import torch
 
 sys.path.insert(0, ".")
-from oracle.vae_oracle import synthetic_vae_params  # noqa: E402  (weights only)
+from realtime_video_b200.factory import synthetic_vae_params  # noqa: E402
 from realtime_video_b200 import ops  # noqa: E402
 from realtime_video_b200.vae import VAEDecoderWrapper  # noqa: E402
 

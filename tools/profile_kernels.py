@@ -17,6 +17,13 @@ if which == "gemm":
     o = torch.empty(L, FF, device=dev, dtype=torch.bfloat16)
     for _ in range(4):
         ops.gemm(a, w, b, epilogue=ops.EPI_BIAS_GELU, out=o)
+elif which == "gemm1":   # N = 5120 (o / cross-attn q,o / ffn.2 shapes): the 1-CTA kernel
+    a = torch.randn(L, FF, device=dev, dtype=torch.bfloat16)
+    w = torch.randn(D, FF, device=dev, dtype=torch.bfloat16) * 0.02
+    b = torch.zeros(D, device=dev, dtype=torch.bfloat16)
+    o = torch.empty(L, D, device=dev, dtype=torch.bfloat16)
+    for _ in range(4):
+        ops.gemm(a, w, b, out=o)
 elif which == "attn":
     q = torch.randn(L, D, device=dev, dtype=torch.bfloat16)
     k = torch.randn(2 * L, D, device=dev, dtype=torch.bfloat16)
