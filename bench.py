@@ -367,21 +367,35 @@ def main():
     if rank != 0:
         return
     peaks = measured_peaks()
-    # roofline of the dominant kernel (tcgen05 GEMM): algorithmic FLOPs / CUDA-event time of its launches
+    # roofline of the dominant kernel family (tcgen05 GEMMs): algorithmic FLOPs / CUDA-event time of its
+    # launches, plus the split between the two kernels behind kr_gemm (CTA-pair / single-CTA)
     gem = prof.get("gemm", {"flops": 0.0, "ms": 0.0, "n": 0})
     att = prof.get("attention", {"flops": 0.0, "ms": 0.0, "n": 0})
     achieved = gem["flops"] / (gem["ms"] * 1e-3) / 1e12 if gem["ms"] > 0 else None
-    traffic = None
+    traffic_db = {}
     tp = ROOT / "profiles" / "r01_gemm_traffic.json"
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+            traffic_db = json.loads(tp.read_text())
         except Exception:  # noqa: BLE001
-            traffic = None
-    roofline = {"bound": "tensor", "kernel": "gemm_tn_kernel (tcgen05, all DiT linears)", "achieved": achieved,
+            traffic_db = {}
+    by_kernel = {}
+    for name in ("gemm2_tn_kernel", "gemm_tn_kernel"):
+        g = prof.get("gemm/" + name)
+        if g and g["ms"] > 0:
+            a = g["flops"] / (g["ms"] * 1e-3) / 1e12
+            by_kernel[name] = {"achieved": a, "frac": a / peaks["tensor"], "launches_timed": g["n"],
+                               "share_of_step": g["ms"] / ms if ms > 0 else None,
+                               "traffic": traffic_db.get(name, {}).get("dram_bytes_per_launch")}
+    dominant = max(by_kernel, key=lambda k: by_kernel[k]["share_of_step"] or 0.0) if by_kernel else None
+    roofline = {"bound": "tensor", "kernel": "kr_gemm (tcgen05: gemm2_tn_kernel CTA-pair + gemm_tn_kernel, all DiT linears)",
+                "achieved": achieved,
                 "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": (achieved / peaks["tensor"]) if achieved else None,
-                "traffic": traffic, "peak_source": peaks["source"], "launches_timed": gem["n"],
+                "traffic": traffic_db.get(dominant, {}).get("dram_bytes_per_launch") if dominant else None,
+                "traffic_kernel": dominant,
+                "peak_source": peaks["source"], "launches_timed": gem["n"],
                 "share_of_step": (gem["ms"] / (ms / 1.0)) if ms > 0 else None,
+                "by_kernel": by_kernel,
                 "attention": {"achieved": att["flops"] / (att["ms"] * 1e-3) / 1e12 if att["ms"] > 0 else None,
                               "unit": "TFLOP/s", "launches_timed": att["n"],
                               "share_of_step": att["ms"] / ms if ms > 0 else None}}

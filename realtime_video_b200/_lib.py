@@ -91,6 +91,7 @@ _sz = ctypes.c_size_t
 
 # name -> argtypes; every function returns int except where noted
 SIGNATURES = {
+    "kr_gemm_kernel_id": [_i, _i, _i, _i],
     "kr_gemm": [_i, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _f, _vp, _i, _i,
                 _i, _vp],
     "kr_attn_fwd": [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _f, _i, _i, _i, _i, _vp],

@@ -342,6 +342,12 @@ static int dispatch_epi(int epi, const void* a, int lda, const void* w, int ldw,
 }
 
 // dtype: 0 = bf16, 1 = fp16
+// Which kernel serves this shape: true = CTA-pair kernel (kr_gemm2.cu), false = the 1-CTA kernel below.
+bool gemm_uses_pair(int epi, int M, int N, int K) {
+  static const int g2_mode = [] { const char* e = getenv("KR_GEMM2"); return e != nullptr ? atoi(e) : 1; }();
+  return g2_mode > 0 && epi != EPI_F32 && N % 256 == 0 && (g2_mode == 2 || gemm2_preferred(M, N, K));
+}
+
 int gemm_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, const GemmParams& p,
             cudaStream_t stream) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) {
@@ -367,10 +373,7 @@ int gemm_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, 
   }
   // wide projections: CTA-pair kernel (KR_GEMM2=0 disables it)
   // KR_GEMM2: 0 = never, 1 = where its wave efficiency wins (default), 2 = whenever N % 256 == 0 (tests)
-  static const int g2_mode = [] { const char* e = getenv("KR_GEMM2"); return e != nullptr ? atoi(e) : 1; }();
-  if (g2_mode > 0 && epi != EPI_F32 && p.N % 256 == 0 &&
-      (g2_mode == 2 || gemm2_preferred(p.M, p.N, p.K)))
-    return gemm2_tn(dtype, epi, a, lda, w, ldw, p, stream);
+  if (gemm_uses_pair(epi, p.M, p.N, p.K)) return gemm2_tn(dtype, epi, a, lda, w, ldw, p, stream);
   int bn;
   if (p.N % 256 == 0) bn = 256;
   else if (p.N % 128 == 0) bn = 128;

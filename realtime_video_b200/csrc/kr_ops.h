@@ -39,6 +39,7 @@ int gemm_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, 
 int gemm2_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, const GemmParams& p,
              cudaStream_t stream);
 bool gemm2_preferred(int M, int N, int K);
+bool gemm_uses_pair(int epi, int M, int N, int K);
 
 struct AttnParams {
   void* out;           // [Lq, heads*128] 16-bit

@@ -53,8 +53,8 @@ def profile_end() -> dict:
 
 
 class _Timed:
-    def __init__(self, family: str, flops: float):
-        self.family, self.flops = family, flops
+    def __init__(self, family: str, flops: float, sub: Optional[str] = None):
+        self.family, self.flops, self.sub = family, flops, sub
 
     def __enter__(self):
         if _prof is not None:
@@ -67,6 +67,8 @@ class _Timed:
         if _prof is not None:
             self.b.record()
             _prof.setdefault(self.family, []).append((self.a, self.b, self.flops))
+            if self.sub is not None:
+                _prof.setdefault(self.family + "/" + self.sub, []).append((self.a, self.b, self.flops))
         return False
 
 
@@ -130,7 +132,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         _req(out2, "out2", a.dtype)
         _, ldc2 = _rows2d(out2, "out2")
     lib = _lib.load()
-    with _Timed("gemm", 2.0 * M * N * K):
+    with _Timed("gemm", 2.0 * M * N * K, sub=("gemm2_tn_kernel" if _prof is not None and
+                                              lib.kr_gemm_kernel_id(epilogue, M, N, K) == 2 else "gemm_tn_kernel")):
         rc = lib.kr_gemm(_DT[a.dtype], epilogue, a.data_ptr(), lda, w.data_ptr(), w.stride(0),
                          _ptr(bias), out.data_ptr(), ldc, M, N, K, _ptr(residual), ldr, _ptr(gate), gs,
                          rows_per_gate, alpha, _ptr(out2), ldc2, n_split, row_offset, _stream())
