@@ -388,7 +388,7 @@ def main():
                                "share_of_step": g["ms"] / ms if ms > 0 else None,
                                "traffic": traffic_db.get(name, {}).get("dram_bytes_per_launch")}
     dominant = max(by_kernel, key=lambda k: by_kernel[k]["share_of_step"] or 0.0) if by_kernel else None
-    roofline = {"bound": "tensor", "kernel": "kr_gemm (tcgen05: gemm2_tn_kernel CTA-pair + gemm_tn_kernel, all DiT linears)",
+    roofline = {"bound": "tensor", "kernel": "kr_gemm (tcgen05: gemm2_tn_kernel CTA-pair + gemm_tn_kernel single-CTA, all DiT linears)",
                 "achieved": achieved,
                 "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": (achieved / peaks["tensor"]) if achieved else None,
                 "traffic": traffic_db.get(dominant, {}).get("dram_bytes_per_launch") if dominant else None,

@@ -60,9 +60,9 @@ int kr_gemm(int dtype, int epilogue, const void* a, int lda, const void* w, int 
             int ldr, const void* gate, int gate_stride, int rows_per_gate, float alpha,
             void* out2, int ldc2, int n_split, int row_offset, void* stream);
 
-/* Which kernel kr_gemm launches for this epilogue and shape: 2 = the CTA-pair kernel
- * (tcgen05.mma.cta_group::2, 256x256 tiles), 1 = the single-CTA kernel.  Host-only query (no launch),
- * used by bench.py to attribute launch time per kernel. */
+/* Which kernel kr_gemm launches for this epilogue and shape: 1 = the single-CTA kernel, 2 = the CTA-pair
+ * kernel (tcgen05.mma.cta_group::2, 256x256 tiles).  Host-only query (no launch), used by bench.py to
+ * attribute launch time per kernel. */
 int kr_gemm_kernel_id(int epilogue, int M, int N, int K);
 
 /* softmax(scale * q k^T) v, head_dim 128, [L, heads, 128] layout, bf16/fp16, fp32 softmax.

@@ -19,7 +19,7 @@ extern "C" {
 int kr_version(void) { return 100; }
 const char* kr_last_error(void) { return kr::last_error(); }
 
-int kr_gemm_kernel_id(int epilogue, int M, int N, int K) { return kr::gemm_uses_pair(epilogue, M, N, K) ? 2 : 1; }
+int kr_gemm_kernel_id(int epilogue, int M, int N, int K) { return kr::gemm_plan(epilogue, M, N, K) + 1; }
 
 int kr_gemm(int dtype, int epilogue, const void* a, int lda, const void* w, int ldw,
             const void* bias, void* out, int ldc, int M, int N, int K, const void* residual,

@@ -342,38 +342,34 @@ static int dispatch_epi(int epi, const void* a, int lda, const void* w, int ldw,
 }
 
 // dtype: 0 = bf16, 1 = fp16
-// Which kernel serves this shape: true = CTA-pair kernel (kr_gemm2.cu), false = the 1-CTA kernel below.
-bool gemm_uses_pair(int epi, int M, int N, int K) {
-  static const int g2_mode = [] { const char* e = getenv("KR_GEMM2"); return e != nullptr ? atoi(e) : 1; }();
-  return g2_mode > 0 && epi != EPI_F32 && N % 256 == 0 && (g2_mode == 2 || gemm2_preferred(M, N, K));
+// Which kernel serves a shape.  Costs are per-SM tile-times in units of one CTA-pair tile (a single-CTA
+// 128x256 tile is the same work per SM but runs at ~0.88 instead of ~0.98 of the tensor peak -> 1.12):
+//   0  the single-CTA kernel below                  ceil(tiles128 / SMs) * 1.12
+//   1  the CTA-pair kernel (kr_gemm2.cu)            ceil(tiles256 / pairs)
+// M = 4680: N = 15360 -> 16 vs 16.8, N = 13824 -> 14 vs 15.7 (pair); N = 5120 -> 6 vs 5.6 (single CTA: 380
+// pair tiles are 5.14 waves of 74 pairs).  A hybrid plan (pair kernel on the first 4608 rows, single-CTA
+// kernel on the last 72 rows on a side stream so its 20 tiles fill the SMs the pair kernel's partial last
+// wave leaves idle; predicted 5.1) was built and measured: 1406 vs 1426 TF/s on ffn.2, 1491 vs 1505 on
+// to_qkv, 16.21 / 16.12 vs 16.23 / 16.26 fps in same-box bench runs -> not kept
+// (profiles/r01_gemm_hybrid_plan_*.log).
+// KR_GEMM2: 0 = never the pair kernel, 1 = by cost (default), 2 = pair whenever N % 256 == 0 (tests)
+int gemm_plan(int epi, int M, int N, int K) {
+  static const int mode = [] { const char* e = getenv("KR_GEMM2"); return e != nullptr ? atoi(e) : 1; }();
+  if (mode <= 0 || epi == EPI_F32 || N % 256 != 0 || K < 256) return 0;
+  if (mode == 2) return 1;
+  const int sms = sm_count(), pairs = sms / 2, nb = N / 256;
+  const long tiles1 = static_cast<long>((M + 127) / 128) * nb;
+  const double cost1 = static_cast<double>((tiles1 + sms - 1) / sms) * 1.12;
+  const long tiles_f = static_cast<long>((M + 255) / 256) * nb;
+  if (tiles_f < 4L * pairs) return 0;
+  const double cost_f = static_cast<double>((tiles_f + pairs - 1) / pairs);
+  return cost_f < cost1 ? 1 : 0;
 }
+bool gemm_uses_pair(int epi, int M, int N, int K) { return gemm_plan(epi, M, N, K) != 0; }
 
-int gemm_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, const GemmParams& p,
-            cudaStream_t stream) {
-  if (p.M <= 0 || p.N <= 0 || p.K <= 0) {
-    set_last_error("gemm: non-positive shape M=%d N=%d K=%d", p.M, p.N, p.K);
-    return KR_ERR_INVALID_ARG;
-  }
-  if (p.K % 8 != 0 || p.N % 32 != 0 || lda % 8 != 0 || ldw % 8 != 0 || p.ldc % 8 != 0) {
-    set_last_error("gemm: unsupported shape M=%d N=%d K=%d (need K%%8==0, N%%32==0, ld%%8==0)",
-                   p.M, p.N, p.K);
-    return KR_ERR_UNSUPPORTED_SHAPE;
-  }
-  if ((epi == EPI_BIAS_GATE_RES || epi == EPI_BIAS_RES) && p.residual == nullptr) {
-    set_last_error("gemm: residual epilogue without residual pointer");
-    return KR_ERR_INVALID_ARG;
-  }
-  if (p.out2 != nullptr && (p.n_split % 256 != 0 || p.ldc2 % 8 != 0 || epi == EPI_F32)) {
-    set_last_error("gemm: split output needs n_split %% 256 == 0, ldc2 %% 8 == 0 and a 16-bit epilogue");
-    return KR_ERR_INVALID_ARG;
-  }
-  if (epi == EPI_BIAS_GATE_RES && (p.gate == nullptr || p.rows_per_gate <= 0)) {
-    set_last_error("gemm: gate epilogue without gate pointer / rows_per_gate");
-    return KR_ERR_INVALID_ARG;
-  }
-  // wide projections: CTA-pair kernel (KR_GEMM2=0 disables it)
-  // KR_GEMM2: 0 = never, 1 = where its wave efficiency wins (default), 2 = whenever N % 256 == 0 (tests)
-  if (gemm_uses_pair(epi, p.M, p.N, p.K)) return gemm2_tn(dtype, epi, a, lda, w, ldw, p, stream);
+namespace {
+int gemm_single(int dtype, int epi, const void* a, int lda, const void* w, int ldw, const GemmParams& p,
+                cudaStream_t stream) {
   int bn;
   if (p.N % 256 == 0) bn = 256;
   else if (p.N % 128 == 0) bn = 128;
@@ -402,6 +398,35 @@ int gemm_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, 
       set_last_error("gemm: N=%d not a multiple of 32", p.N);
       return KR_ERR_UNSUPPORTED_SHAPE;
   }
+}
+}  // namespace
+
+int gemm_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, const GemmParams& p,
+            cudaStream_t stream) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) {
+    set_last_error("gemm: non-positive shape M=%d N=%d K=%d", p.M, p.N, p.K);
+    return KR_ERR_INVALID_ARG;
+  }
+  if (p.K % 8 != 0 || p.N % 32 != 0 || lda % 8 != 0 || ldw % 8 != 0 || p.ldc % 8 != 0) {
+    set_last_error("gemm: unsupported shape M=%d N=%d K=%d (need K%%8==0, N%%32==0, ld%%8==0)",
+                   p.M, p.N, p.K);
+    return KR_ERR_UNSUPPORTED_SHAPE;
+  }
+  if ((epi == EPI_BIAS_GATE_RES || epi == EPI_BIAS_RES) && p.residual == nullptr) {
+    set_last_error("gemm: residual epilogue without residual pointer");
+    return KR_ERR_INVALID_ARG;
+  }
+  if (p.out2 != nullptr && (p.n_split % 256 != 0 || p.ldc2 % 8 != 0 || epi == EPI_F32)) {
+    set_last_error("gemm: split output needs n_split %% 256 == 0, ldc2 %% 8 == 0 and a 16-bit epilogue");
+    return KR_ERR_INVALID_ARG;
+  }
+  if (epi == EPI_BIAS_GATE_RES && (p.gate == nullptr || p.rows_per_gate <= 0)) {
+    set_last_error("gemm: gate epilogue without gate pointer / rows_per_gate");
+    return KR_ERR_INVALID_ARG;
+  }
+  const int plan = gemm_plan(epi, p.M, p.N, p.K);
+  if (plan == 1) return gemm2_tn(dtype, epi, a, lda, w, ldw, p, stream);
+  return gemm_single(dtype, epi, a, lda, w, ldw, p, stream);
 }
 
 }  // namespace kr

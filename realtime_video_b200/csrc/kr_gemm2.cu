@@ -368,21 +368,6 @@ static int launch_gemm2(const void* a, int lda, const void* w, int ldw, const Ge
   return KR_OK;
 }
 
-// Is the CTA-pair kernel expected to beat the single-CTA one for this shape?  Pair tiles are
-// 256x256 over sm_count/2 pairs: use it when its last wave is well filled.
-bool gemm2_preferred(int M, int N, int K) {
-  if (N % G2_BLOCK_N != 0 || K < 2 * G2_BLOCK_K) return false;
-  const int pairs = sm_count() / 2;
-  const long tiles2 = static_cast<long>((M + 255) / 256) * (N / 256);
-  if (tiles2 < 4L * pairs) return false;
-  const long waves2 = (tiles2 + pairs - 1) / pairs;
-  const double eff2 = static_cast<double>(tiles2) / static_cast<double>(waves2 * pairs);
-  const long tiles1 = static_cast<long>((M + 127) / 128) * (N / 256);
-  const long waves1 = (tiles1 + sm_count() - 1) / sm_count();
-  const double eff1 = static_cast<double>(tiles1) / static_cast<double>(waves1 * sm_count());
-  return eff2 * 1.10 > eff1;     // pair tiles run ~10-15 % faster per tile (operand traffic halved)
-}
-
 int gemm2_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, const GemmParams& p,
              cudaStream_t stream) {
   const bool bf = dtype == 0;

@@ -38,8 +38,8 @@ int gemm_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, 
 // CTA-pair (cta_group::2, 256x256 tiles) variant, kr_gemm2.cu
 int gemm2_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, const GemmParams& p,
              cudaStream_t stream);
-bool gemm2_preferred(int M, int N, int K);
 bool gemm_uses_pair(int epi, int M, int N, int K);
+int gemm_plan(int epi, int M, int N, int K);   // 0 single-CTA kernel, 1 CTA-pair kernel
 
 struct AttnParams {
   void* out;           // [Lq, heads*128] 16-bit

@@ -52,6 +52,10 @@ def profile_end() -> dict:
     return out
 
 
+# kr_gemm_kernel_id -> label used in the per-kernel timing split
+_GEMM_KERNELS = {1: "gemm_tn_kernel", 2: "gemm2_tn_kernel"}
+
+
 class _Timed:
     def __init__(self, family: str, flops: float, sub: Optional[str] = None):
         self.family, self.flops, self.sub = family, flops, sub
@@ -132,8 +136,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         _req(out2, "out2", a.dtype)
         _, ldc2 = _rows2d(out2, "out2")
     lib = _lib.load()
-    with _Timed("gemm", 2.0 * M * N * K, sub=("gemm2_tn_kernel" if _prof is not None and
-                                              lib.kr_gemm_kernel_id(epilogue, M, N, K) == 2 else "gemm_tn_kernel")):
+    with _Timed("gemm", 2.0 * M * N * K,
+                sub=_GEMM_KERNELS[lib.kr_gemm_kernel_id(epilogue, M, N, K)] if _prof is not None else None):
         rc = lib.kr_gemm(_DT[a.dtype], epilogue, a.data_ptr(), lda, w.data_ptr(), w.stride(0),
                          _ptr(bias), out.data_ptr(), ldc, M, N, K, _ptr(residual), ldr, _ptr(gate), gs,
                          rows_per_gate, alpha, _ptr(out2), ldc2, n_split, row_offset, _stream())
