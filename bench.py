@@ -259,6 +259,7 @@ def main():
                          "sequence-parallel over all GPUs (realtime_video_b200/parallel.py)")
     ap.add_argument("--layers", type=int, default=LAYERS, help=argparse.SUPPRESS)      # debugging only
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-egress", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -360,6 +361,37 @@ def main():
     h2d = host_noise[:, :nf].numel() * host_noise.element_size()
     d2h = host_px.numel() * host_px.element_size()
 
+    # ---------------- same end-to-end loop with the byte egress kernel ----------------
+    # kr_frames_to_rgb8 does the reference's host-side normalise + to_pil_image conversion on the device, so
+    # uint8 [12, H, W, 3] (14.4 MB) instead of fp32 (57.5 MB) crosses PCIe.  Reported next to `e2e`, which keeps
+    # the reference's own fp32 download.
+    egress = None
+    if decode and not sp_mode and not args.no_egress:
+        sess3 = GenerationSession(GenerateParams(num_blocks=W + K, seed=2042 + rank), models,
+                                  prompt_embeds=pe, device=dev, decode=True)
+        host_noise3 = sess3.noise.cpu().pin_memory()
+        host_rgb = torch.empty(1, 12, 480, 832, 3, dtype=torch.uint8).pin_memory()
+        dev_rgb = torch.empty(1, 12, 480, 832, 3, dtype=torch.uint8, device=dev)
+        with torch.inference_mode():
+            for _ in range(W):
+                sess3.generate_block()
+            barrier()
+            u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            u0.record()
+            for _ in range(K):
+                s3 = sess3.current_start_frame
+                sess3.noise[:, s3:s3 + nf].copy_(host_noise3[:, s3:s3 + nf], non_blocking=True)
+                px3 = sess3.generate_block()
+                ops.frames_to_rgb8(px3, out=dev_rgb)
+                host_rgb.copy_(dev_rgb, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            u1.record()
+            barrier()
+        ms_rgb = max_over_ranks(u0.elapsed_time(u1))
+        egress = {"value": streams * K * FRAMES_PER_STEP / (ms_rgb / 1e3), "unit": "frames/s",
+                  "d2h_bytes_per_step": host_rgb.numel(), "ms_per_step": ms_rgb / K,
+                  "what": "e2e loop with kr_frames_to_rgb8 on the device and a uint8 [12,480,832,3] download"}
+
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -421,6 +453,7 @@ def main():
                        f"VAE decode on rank 0" if sp_mode else f"{world} independent replicas (path does not shard)"),
                    "l2": "weights (28 GB/pass) and KV cache exceed the 126 MB L2 every step; no flush needed",
                    "dit_tflop_per_step": block_tflop},
+        "egress_rgb8": egress,
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": launches,

@@ -150,6 +150,13 @@ int kr_vae_scale_input(int dtype, const void* z, long zt, long zc, long zh, long
 int kr_softmax_rows(int dtype, const float* s, long ld, void* p, long ldo, int rows, int cols,
                     void* stream);
 
+/* Frame egress: decoder pixels fp32 [frames, 3, H, W] in [-1, 1] -> packed RGB bytes
+ * [frames, H, W, 3], byte = trunc(clamp((x + 1) * 0.5, 0, 1) * 255) in fp32 — the arithmetic the reference
+ * runs on the host after the device->host copy (release_server.py:979-983 `add_(1.0).mul_(0.5).clamp_(0,1)`,
+ * then torchvision `to_pil_image`: `.mul(255).byte()`), so 14.4 MB instead of 57.5 MB leave the device per
+ * 12-frame 832x480 block.  `pixels` must be contiguous. */
+int kr_frames_to_rgb8(const float* pixels, unsigned char* rgb, int frames, int height, int width, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,6 +109,7 @@ SIGNATURES = {
     "kr_vae_upsample2x": [_vp, _vp, _i, _i, _i, _i, _vp],
     "kr_vae_scale_input": [_i, _vp, _l, _l, _l, _l, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "kr_softmax_rows": [_i, _vp, _l, _vp, _l, _i, _i, _vp],
+    "kr_frames_to_rgb8": [_vp, _vp, _i, _i, _i, _vp],
 }
 
 

@@ -154,4 +154,9 @@ int kr_softmax_rows(int dtype, const float* s, long ld, void* p, long ldo, int r
   return kr::softmax_rows(dtype, s, ld, p, ldo, rows, cols, static_cast<cudaStream_t>(stream));
 }
 
+int kr_frames_to_rgb8(const float* pixels, uint8_t* rgb, int frames, int height, int width, void* stream) {
+  KR_REQUIRE(pixels && rgb, "null pointer");
+  return kr::frames_to_rgb8(pixels, rgb, frames, height, width, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

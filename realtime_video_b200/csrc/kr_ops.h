@@ -110,4 +110,5 @@ int vae_scale_input(int dtype, const void* z, long zt, long zc, long zh, long zw
                     int W, cudaStream_t stream);
 int softmax_rows(int dtype, const float* s, long ld, void* pout, long ldo, int rows, int cols,
                  cudaStream_t stream);
+int frames_to_rgb8(const float* pixels, uint8_t* rgb, int frames, int height, int width, cudaStream_t stream);
 }  // namespace kr

@@ -389,3 +389,25 @@ def softmax_rows(s: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     _lib.check(rc, "kr_softmax_rows")
     _count()
     return out
+
+
+def frames_to_rgb8(pixels: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Decoder output fp32 [..., T, 3, H, W] in [-1, 1] -> uint8 [..., T, H, W, 3] (PIL 'RGB' layout), the bytes
+    the reference produces on the host with add_(1).mul_(0.5).clamp_(0, 1) + to_pil_image
+    (release_server.py:979-983)."""
+    _req(pixels, "pixels", torch.float32)
+    if pixels.dim() < 4 or pixels.shape[-3] != 3 or not pixels.is_contiguous():
+        raise _lib.KreaB200Error("frames_to_rgb8: expected contiguous fp32 [..., T, 3, H, W]")
+    lead, (H, W) = pixels.shape[:-3], pixels.shape[-2:]
+    T = 1
+    for d in lead:
+        T *= int(d)
+    if out is None:
+        out = torch.empty(*lead, H, W, 3, dtype=torch.uint8, device=pixels.device)
+    elif out.dtype != torch.uint8 or not out.is_contiguous() or out.numel() != T * H * W * 3:
+        raise _lib.KreaB200Error("frames_to_rgb8: out must be contiguous uint8 [..., T, H, W, 3]")
+    lib = _lib.load()
+    rc = lib.kr_frames_to_rgb8(pixels.data_ptr(), out.data_ptr(), T, H, W, _stream())
+    _lib.check(rc, "kr_frames_to_rgb8")
+    _count()
+    return out
