@@ -61,3 +61,17 @@ def test_product_never_imports_the_oracle():
     for f in pkg.rglob("*.py"):
         src = f.read_text()
         assert "from oracle" not in src and "import oracle" not in src, f"{f} imports the oracle"
+
+
+def test_gemm_kernel_plan_for_the_bench_shapes():
+    """Host-only query: which kernel kr_gemm serves a shape with on a 148-SM part (the CPU box falls back to 148).
+    M = 4680 token rows: the wide projections go to the CTA-pair kernel, the N = 5120 shapes (380 pair tiles =
+    5.14 waves of 74 pairs) stay on the single-CTA kernel, small problems never use the pair kernel."""
+    from realtime_video_b200 import _lib
+    lib = _lib.load()
+    assert lib.kr_gemm_kernel_id(0, 4680, 15360, 5120) == 2      # to_qkv
+    assert lib.kr_gemm_kernel_id(1, 4680, 13824, 5120) == 2      # ffn.0 + GELU
+    assert lib.kr_gemm_kernel_id(2, 4680, 5120, 5120) == 1       # o + gate/residual
+    assert lib.kr_gemm_kernel_id(2, 4680, 5120, 13824) == 1      # ffn.2 + gate/residual
+    assert lib.kr_gemm_kernel_id(0, 512, 10240, 4096) == 1       # cross-attention k/v of the prompt
+    assert lib.kr_gemm_kernel_id(4, 4680, 15360, 5120) == 1      # fp32-output epilogue: single-CTA only
