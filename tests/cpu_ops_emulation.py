@@ -1,0 +1,127 @@
+"""fp32 torch stand-ins for the ``realtime_video_b200.ops`` functions the DiT host schedule calls — TEST
+INFRASTRUCTURE: lets ``-m "not gpu"`` tests execute realtime_video_b200/dit.py's HOST logic (cache-slot
+arithmetic, rolling eviction, split QKV output, block-mask / padded-key bookkeeping, cross-attention cache,
+per-frame modulation indexing, unpatchify) on the CPU and compare it with the reference goldens.  Each function
+implements the documented contract of the C-ABI entry point of the same name (include/krea_b200.h) without the
+16-bit rounding points; nothing here is reachable from the product path (tests monkeypatch ``dit.ops``)."""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from oracle import dit_oracle as O
+
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES, EPI_BIAS_RES, EPI_F32 = 0, 1, 2, 3, 4
+launch_count = 0
+
+
+def _store(out: Optional[torch.Tensor], val: torch.Tensor) -> torch.Tensor:
+    if out is None:
+        return val
+    out.copy_(val)
+    return out
+
+
+def gemm(a, w, bias=None, *, epilogue=EPI_BIAS, out=None, residual=None, gate=None, rows_per_gate=0, alpha=1.0,
+         out2=None, n_split=0, row_offset=0):
+    y = a.float() @ w.float().t()
+    if bias is not None:
+        y = y + bias.float()
+    if epilogue == EPI_BIAS_GELU:
+        y = F.gelu(y, approximate="tanh")
+    elif epilogue == EPI_BIAS_GATE_RES:
+        rows = torch.arange(a.shape[0]) + row_offset
+        y = residual.float() + y * gate.float()[rows // rows_per_gate]
+    elif epilogue == EPI_BIAS_RES:
+        y = residual.float() + y
+    elif epilogue == EPI_F32:
+        return _store(out, y * alpha)
+    y = y.to(a.dtype)
+    if out2 is not None:
+        out2.copy_(y[:, n_split:])
+        y = y[:, :n_split]
+    return _store(out, y)
+
+
+def attention(q, k, v, *, heads, out=None, softmax_scale=None, block_len=0, window=0, pad_keys=0):
+    Lq, Lkv = q.shape[0], k.shape[0]
+    d = q.shape[-1] // heads
+    scale = softmax_scale if softmax_scale is not None else 1.0 / math.sqrt(d)
+    qf = q.float().reshape(Lq, heads, d).transpose(0, 1)
+    kf = k.float().reshape(Lkv, heads, d).transpose(0, 1)
+    vf = v.float().reshape(Lkv, heads, d).transpose(0, 1)
+    s = qf @ kf.transpose(1, 2) * scale                                   # [heads, Lq, Lkv]
+    n_ph = torch.zeros(Lq)
+    if block_len > 0:
+        qi = torch.arange(Lq)[:, None]
+        ki = torch.arange(Lkv)[None, :]
+        hi = (qi // block_len + 1) * block_len
+        ok = ki < hi
+        if window > 0:
+            ok = ok & (ki >= hi - window)
+        s = s.masked_fill(~ok, float("-inf"))
+        # zero-padded phantom keys of the FlexAttention path (score 0, value 0) for rows whose block runs past Lkv
+        n_ph = (hi[:, 0] - Lkv).clamp(min=0, max=pad_keys).float()
+    m = torch.maximum(s.amax(dim=-1), torch.where(n_ph > 0, 0.0, float("-inf"))[None])
+    p = torch.exp(s - m[..., None])
+    den = p.sum(-1) + n_ph[None] * torch.exp(-m)
+    o = (p @ vf) / den[..., None]
+    return _store(out, o.transpose(0, 1).reshape(Lq, heads * d).to(q.dtype))
+
+
+def ln_modulate(x, *, eps, weight=None, bias=None, mod=None, shift_idx=0, scale_idx=1, rows_per_frame=0, out=None,
+                row_offset=0):
+    y = F.layer_norm(x.float(), (x.shape[-1],), None if weight is None else weight.float(),
+                     None if bias is None else bias.float(), eps)
+    if mod is not None:
+        fr = (torch.arange(x.shape[0]) + row_offset) // rows_per_frame
+        y = y * (1 + mod.float()[fr, scale_idx]) + mod.float()[fr, shift_idx]
+    return _store(out, y.to(x.dtype))
+
+
+def rmsnorm(x, weight, eps, out=None):
+    xf = x.float()
+    return _store(out, (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps) * weight.float()).to(x.dtype))
+
+
+def qkv_norm_rope(q, k, v, wq, wk, q_out, k_out, v_out, rope, *, head_dim, grid_h, grid_w, start_frame, eps,
+                  row_offset=0):
+    assert row_offset == 0, "the CPU stand-in covers the single-GPU schedule"
+    rows, D = q.shape
+    n = D // head_dim
+    f = rows // (grid_h * grid_w)
+    ang = O.rope_table(head_dim)
+    for src, w, dst in ((q, wq, q_out), (k, wk, k_out)):
+        y = rmsnorm(src, w, eps).reshape(rows, n, head_dim)
+        dst.copy_(O.rope_apply(y, (f, grid_h, grid_w), ang, start_frame).reshape(rows, D))
+    if v is not None:
+        v_out.copy_(v)
+
+
+def add_modulation(modulation, e0, out=None):
+    return _store(out, (modulation.float() + e0.float()).to(e0.dtype))
+
+
+def activation(x, kind):
+    return (F.silu(x.float()) if kind == "silu" else F.gelu(x.float(), approximate="tanh")).to(x.dtype)
+
+
+def patchify(x):
+    """[C, F, H, W] -> [F*(H/2)*(W/2), C*4]: Conv3d(kernel = stride = (1, 2, 2)) im2col, weight.view(dim, -1)
+    column order (c, kh, kw)."""
+    C, Fr, H, W = x.shape
+    p = x.reshape(C, Fr, H // 2, 2, W // 2, 2).permute(1, 2, 4, 0, 3, 5)
+    return p.reshape(Fr * (H // 2) * (W // 2), C * 4).contiguous()
+
+
+def unpatchify_x0(head_out, xt, sigma, C, Fr, H, W):
+    """causal_model.py:1126-1149: head columns are (kh, kw, c); x0 = xt - sigma_f * flow in float64."""
+    u = head_out.reshape(Fr, H // 2, W // 2, 2, 2, C)
+    flow = u.permute(0, 5, 1, 3, 2, 4).reshape(Fr, C, H, W).contiguous()
+    x0 = None
+    if xt is not None:
+        x0 = (xt.double() - sigma.double().view(-1, 1, 1, 1) * flow.double()).to(flow.dtype)
+    return flow, x0
