@@ -89,14 +89,22 @@ def rmsnorm(x, weight, eps, out=None):
 
 def qkv_norm_rope(q, k, v, wq, wk, q_out, k_out, v_out, rope, *, head_dim, grid_h, grid_w, start_frame, eps,
                   row_offset=0):
-    assert row_offset == 0, "the CPU stand-in covers the single-GPU schedule"
+    """RMSNorm over all D channels, then RoPE per head: pair j of a head rotates by the angle of the token's
+    frame (first c - 2(c//3) pairs), row (next c//3) or column (last c//3) position; the token of local row r is
+    global row r + row_offset of the [frames, grid_h, grid_w] raster (causal_model.py:143-171)."""
     rows, D = q.shape
-    n = D // head_dim
-    f = rows // (grid_h * grid_w)
-    ang = O.rope_table(head_dim)
+    n, c = D // head_dim, head_dim // 2
+    fs = grid_h * grid_w
+    r = torch.arange(rows) + row_offset
+    tab = O.rope_table(head_dim)                                   # float64 [1024, c]
+    ct, ch = c - 2 * (c // 3), c // 3
+    ang = torch.cat([tab[r // fs + start_frame, :ct], tab[(r % fs) // grid_w, ct:ct + ch],
+                     tab[r % grid_w, ct + ch:]], dim=-1)[:, None, :]          # [rows, 1, c]
+    cs, sn = torch.cos(ang), torch.sin(ang)
     for src, w, dst in ((q, wq, q_out), (k, wk, k_out)):
-        y = rmsnorm(src, w, eps).reshape(rows, n, head_dim)
-        dst.copy_(O.rope_apply(y, (f, grid_h, grid_w), ang, start_frame).reshape(rows, D))
+        y = rmsnorm(src, w, eps).double().reshape(rows, n, c, 2)
+        y0, y1 = y[..., 0], y[..., 1]
+        dst.copy_(torch.stack([y0 * cs - y1 * sn, y0 * sn + y1 * cs], dim=-1).reshape(rows, D).to(q.dtype))
     if v is not None:
         v_out.copy_(v)
 

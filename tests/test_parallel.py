@@ -63,3 +63,56 @@ def test_rows_heads_all_to_all_gloo(world, L, heads):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, L, heads, ret), nprocs=world, join=True)
     assert [ret.get(r) for r in range(world)] == ["ok"] * world
+
+
+def _sp_model_worker(rank, world, port, ret):
+    """The sequence-parallel branch of dit.py (row shards, head-sharded KV cache, two all-to-alls per layer,
+    row offsets of the modulation / RoPE / gate lookups) on `world` gloo ranks, kernels replaced by the fp32
+    stand-ins: every rank must reproduce the reference's fp32 goldens of the single-GPU schedule."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import realtime_video_b200.dit as dit
+        from realtime_video_b200.parallel import SequenceParallel
+        from tests import cpu_ops_emulation as emu
+        from tests.golden_io import load_npz, rel_l2, weights
+        dit.ops = emu
+        g = load_npz("dit_small.npz")
+        FS = 96
+        m = dit.CausalWanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=128)
+        m.load_state_dict(weights(g, torch.float32), strict=False)
+        m = m.float().eval()
+        for blk in m.blocks:
+            blk.self_attn.fuse_projections()
+        m.sp = SequenceParallel()
+        n, d = m.kv_cache_heads, m.dim // m.num_heads
+        assert n == 2 // world
+        kv = [{"k": torch.zeros(1, 6 * FS, n, d), "v": torch.zeros(1, 6 * FS, n, d),
+               "global_end_index": 0, "local_end_index": 0} for _ in m.blocks]
+        ca = [{"k": torch.zeros(1, 512, 2, d), "v": torch.zeros(1, 512, 2, d), "is_init": False} for _ in m.blocks]
+
+        def fwd(xname, t, start):
+            x = g[xname].float()
+            with torch.no_grad():
+                return m(x[None], t=torch.full((1, x.shape[1]), float(t)), context=g["in/ctx"].float()[None],
+                         seq_len=32760, kv_cache=kv, crossattn_cache=ca, current_start=start)[0]
+
+        for xname, t, start, name in (("in/x0", 1000, 0, "cache/flow1"), ("in/x1", 750, 0, "cache/flow2"),
+                                      ("in/x2", 1000, 3 * FS, "cache/flow3")):
+            r = rel_l2(fwd(xname, t, start), g[f"fp32/{name}"])
+            assert r < 1e-4, (name, r)
+        # my head block of the reference's K cache
+        k_ref = g["fp32/cache/k0"].reshape(-1, 2, d)[:, rank * n:(rank + 1) * n]
+        assert rel_l2(kv[0]["k"][0], k_ref) < 1e-4
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sequence_parallel_dit_schedule_gloo():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_sp_model_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert [ret.get(r) for r in range(world)] == ["ok"] * world
