@@ -133,3 +133,64 @@ def unpatchify_x0(head_out, xt, sigma, C, Fr, H, W):
     if xt is not None:
         x0 = (xt.double() - sigma.double().view(-1, 1, 1, 1) * flow.double()).to(flow.dtype)
     return flow, x0
+
+
+# ---------------------------------------------------------------------------------------------
+# VAE ops (channels-last activations [frames, H, W, C]); contracts: include/krea_b200.h kr_vae_*
+# ---------------------------------------------------------------------------------------------
+def vae_scale_input(z, mean, inv_std, w2, b2, out):
+    """z [T, 16, H, W] -> x = z / inv_std + mean; y = conv2_1x1x1(x); channels-last, zero-padded to out's C."""
+    x = z.float() / inv_std.float().view(1, -1, 1, 1) + mean.float().view(1, -1, 1, 1)
+    y = torch.einsum("oc,tchw->thwo", w2.float(), x) + b2.float()
+    out.zero_()
+    out[..., :y.shape[-1]] = y.to(out.dtype)
+    return out
+
+
+def _rms(y, gamma, silu=True):
+    C = y.shape[-1]
+    o = F.normalize(y, dim=-1) * math.sqrt(C) * gamma.float()[:C]
+    return F.silu(o) if silu else o
+
+
+def vae_conv(x, weight, bias, *, n, cout, T, taps, tile, out_raw=None, out_norm=None, gamma=None, residual=None,
+             out_pix=None, raw_frame_stride=None, sub2=False):
+    """Causal conv as the kernel defines it: x holds kt-1 history frames in front of the T new ones, weight is
+    [rows, kt*kh*kw*cin] with (kt, kh, kw, cin) column order, spatial zero padding, then the fused epilogue."""
+    t_in, H, W, cin = x.shape
+    kt, kh, kw = taps
+    rows = weight.shape[0]
+    w5 = weight.float().reshape(rows, kt, kh, kw, cin).permute(0, 4, 1, 2, 3)
+    xin = F.pad(x.float().permute(3, 0, 1, 2)[None], (kw // 2, kw // 2, kh // 2, kh // 2, 0, 0))
+    y = F.conv3d(xin, w5)[0].permute(1, 2, 3, 0)[:T]                      # [T, H, W, rows]
+    if bias is not None:
+        y = y + bias.float()[:rows]
+    y = y[..., :cout]
+    if sub2:                                                               # stride-2 conv = odd positions
+        y = y[:, 1::2, 1::2]
+    if residual is not None:
+        y = residual[:T].float() + y
+    if out_raw is not None:
+        fr = raw_frame_stride if raw_frame_stride is not None else out_raw.stride(0)
+        dst = torch.as_strided(out_raw, (T, y.shape[1], y.shape[2], y.shape[3]),
+                               (fr, out_raw.stride(-3), out_raw.stride(-2), 1), out_raw.storage_offset())
+        dst.copy_(y.to(out_raw.dtype))
+    if out_norm is not None:
+        out_norm[:T].copy_(_rms(y, gamma).to(out_norm.dtype))
+    if out_pix is not None:
+        out_pix.copy_(y.clamp(-1, 1).permute(0, 3, 1, 2))
+
+
+def vae_rmsnorm_silu(x, gamma, out, silu=True):
+    out.copy_(_rms(x.float(), gamma, silu).to(out.dtype))
+    return out
+
+
+def vae_upsample2x(x, out):
+    out.copy_(x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2))
+    return out
+
+
+def softmax_rows(s, out):
+    out.copy_(torch.softmax(s.float(), dim=-1).to(out.dtype))
+    return out

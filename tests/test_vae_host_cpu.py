@@ -1,0 +1,85 @@
+"""Host logic of realtime_video_b200/vae.py (DecoderEngine / EncoderEngine) executed on the CPU with the
+kernels replaced by the fp32 stand-ins of tests/cpu_ops_emulation.py: persistent conv-input buffers whose two
+leading frames ARE the feature cache, the cache roll, the first-frame sentinel and the ``where`` quirk of the
+up3d time_conv cache, the channel->time interleave, chunking, cache export/import, the single-frame wrapper and
+the first-chunk encoder — against the goldens of the reference's own VAE modules (tests/golden/vae_small.npz).
+Activations are stored in fp16 like the product (the engine picks the dtype); tolerance rel-L2 <= 5e-3."""
+import pytest
+import torch
+
+from oracle.vae_oracle import synthetic_vae_params
+from tests import cpu_ops_emulation as emu
+from tests.golden_io import load_npz, rel_l2
+
+TOL = 5e-3
+
+
+@pytest.fixture(autouse=True)
+def cpu_ops(monkeypatch):
+    import realtime_video_b200.vae as vae
+    monkeypatch.setattr(vae, "ops", emu)
+
+
+@pytest.fixture(scope="module")
+def g():
+    return load_npz("vae_small.npz")
+
+
+def decoder():
+    from realtime_video_b200.vae import VAEDecoderWrapper
+    m = VAEDecoderWrapper()
+    m.load_state_dict(synthetic_vae_params(seed=0), strict=False)
+    return m.half().eval()
+
+
+def test_streaming_decode_three_calls(g):
+    m = decoder()
+    cache = [None] * 55
+    with torch.no_grad():
+        for call, frames in enumerate([9, 12, 4]):
+            px, cache = m(g[f"s8x12/z{call}"].half(), *cache)
+            assert px.dtype == torch.float32 and px.shape[1] == frames
+            r = rel_l2(px, g[f"s8x12/px{call}"])
+            assert r < TOL, f"call {call}: rel_l2={r:.3e}"
+
+
+def test_reset_and_cache_roundtrip(g):
+    m = decoder()
+    z0, z1 = g["s8x12/z0"].half(), g["s8x12/z1"].half()
+    with torch.no_grad():
+        a, cache = m(z0, *([None] * 55))
+        b, _ = m(z1, *cache)
+        a2, cache2 = m(z0, *([None] * 55))
+        b2, _ = m(z1, *[c.clone() if c is not None else None for c in cache2])
+    assert torch.equal(a, a2) and torch.equal(b, b2)
+    with pytest.raises(ValueError, match="partial VAE feature cache"):
+        m(z1, *([cache2[0]] + [None] * 54))
+
+
+def test_single_frame_wrapper(g):
+    from realtime_video_b200.vae import VAEDecoderWrapperSingle
+    m = VAEDecoderWrapperSingle()
+    m.load_state_dict(synthetic_vae_params(seed=0), strict=False)
+    m = m.half().eval()
+    h, w = 8, 12
+    shapes = [(16, h, w)] + [(384, h, w)] * 11 + [(192, 2 * h, 2 * w)] + [(384, 2 * h, 2 * w)] * 6 \
+        + [(192, 4 * h, 4 * w)] * 6 + [(96, 8 * h, 8 * w)] * 7
+    cache = [torch.zeros(1, c, 2, hh, ww, dtype=torch.float16) for (c, hh, ww) in shapes]
+    with torch.no_grad():
+        for i in range(3):
+            px, cache = m(g[f"single8x12/z{i}"].half(), torch.tensor(i == 0), *cache)
+            assert px.shape == (1, 4, 3, 64, 96) and len(cache) == 32
+            r = rel_l2(px.float(), g[f"single8x12/px{i}"])
+            assert r < TOL, f"single frame {i}: rel_l2={r:.3e}"
+
+
+def test_encoder_first_frame(g):
+    from realtime_video_b200.vae import VAEEncoderWrapper
+    m = VAEEncoderWrapper()
+    m.load_state_dict(synthetic_vae_params(seed=0, encoder=True), strict=False)
+    m = m.half().eval()
+    with torch.no_grad():
+        mu, _ = m(g["enc64x96/x"].half(), [None] * 55)
+    assert mu.shape == g["enc64x96/mu"].shape
+    r = rel_l2(mu, g["enc64x96/mu"])
+    assert r < TOL, f"rel_l2={r:.3e}"
