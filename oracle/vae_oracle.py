@@ -136,14 +136,71 @@ from realtime_video_b200.factory import synthetic_vae_params  # noqa: E402,F401 
 
 
 class VAEEncoderOracle:
-    """First-chunk encode (one pixel frame, empty cache): demo_utils/vae_block3.py:136-150,
-    wan/modules/vae.py:301-345 (Encoder3d.forward), :144-172 (Resample downsample: the
-    downsample3d time_conv is skipped while its cache slot is None), WanVAE_.conv1 + chunk +
-    (mu - mean) * 1/std (vae_block3.py:166-172).  Params keyed 'encoder.*', 'conv1.*'."""
+    """VAE encoder restatement.  ``encode_first``: one pixel frame, empty cache (demo_utils/vae_block3.py:136-150).
+    ``forward``: the full streaming wrapper loop (vae_block3.py:141-175: chunks of 1, 4, 4, ... frames, or 4, 4,
+    ... with ``stream=True`` and a warm cache) over ``encoder_chunk`` = Encoder3d.forward with the feature cache
+    (wan/modules/vae.py:301-345; cached causal convs :17-36 / :191-206; Resample downsample2d/3d :144-172 — the
+    downsample3d time_conv (3,1,1)/stride (2,1,1) is skipped while its cache slot is None, afterwards it sees
+    [last cached frame, chunk] and the slot keeps the chunk's last frame), then WanVAE_.conv1, chunk(2)[0] and
+    (mu - mean) * 1/std (vae_block3.py:166-172).  Params keyed 'encoder.*', 'conv1.*'; cache = dict slot -> tensor.
+    Pinned by tests/golden/make_vae_goldens.py and make_vae_encoder_stream_goldens.py (reference run on CPU)."""
 
     def __init__(self, params):
         self.p = params
         self.dec = VAEDecoderOracle(params)     # reuses causal-conv / res / attention restatements
+
+    def encoder_chunk(self, x, cache):
+        """Encoder3d.forward(x [1, 3, t, H, W], feat_cache) -> [1, 32, t', H/8, W/8]."""
+        p, d = self.p, self.dec
+        idx = [0]
+        x = d._cached_conv("encoder.conv1", x, cache, idx)
+        n = 0
+        for i in range(4):
+            for _ in range(2):
+                x = d._res(f"encoder.downsamples.{n}", x, cache, idx)
+                n += 1
+            if i != 3:
+                pre = f"encoder.downsamples.{n}"
+                b, c, t, h, w = x.shape
+                y = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w)
+                y = F.conv2d(F.pad(y, (0, 1, 0, 1)), p[pre + ".resample.1.weight"], p[pre + ".resample.1.bias"], stride=2)
+                x = y.reshape(b, t, c, h // 2, w // 2).permute(0, 2, 1, 3, 4)
+                if i in (1, 2):                                          # downsample3d (vae.py:157-172)
+                    j = idx[0]
+                    if cache.get(j) is None:
+                        cache[j] = x.clone()
+                    else:
+                        last = x[:, :, -1:].clone()
+                        x = F.conv3d(torch.cat([cache[j][:, :, -1:], x], dim=2), p[pre + ".time_conv.weight"],
+                                     p[pre + ".time_conv.bias"], stride=(2, 1, 1))
+                        cache[j] = last
+                    idx[0] += 1
+                n += 1
+        x = d._res("encoder.middle.0", x, cache, idx)
+        x = d._attn("encoder.middle.1", x)
+        x = d._res("encoder.middle.2", x, cache, idx)
+        x = F.silu(rms_norm(x, p["encoder.head.0.gamma"]))
+        return d._cached_conv("encoder.head.2", x, cache, idx)
+
+    def forward(self, z, cache, stream=False):
+        """VAEEncoderWrapper.forward: z [1, 3, T, H, W] pixels, cache dict -> (mu [1, 16, T', H/8, W/8], cache)."""
+        t = z.shape[2]
+        out = None
+        offset = 1
+        for i in range(1 + (t - 1) // 4):
+            if i == 0 and cache.get(0) is None:
+                out = self.encoder_chunk(z[:, :, :1], cache)
+            else:
+                start = i - 1
+                if stream:
+                    offset, start = 0, i
+                o = self.encoder_chunk(z[:, :, offset + 4 * start:offset + 4 * (start + 1)], cache)
+                out = o if (i == 0 and stream) else torch.cat([out, o], dim=2)
+        mu = causal_conv3d(out, self.p["conv1.weight"], self.p["conv1.bias"]).chunk(2, dim=1)[0]
+        dt = mu.dtype
+        mean = torch.tensor(MEAN, dtype=torch.float32).to(dt).view(1, 16, 1, 1, 1)
+        inv_std = (1.0 / torch.tensor(STD, dtype=torch.float32).to(dt)).view(1, 16, 1, 1, 1)
+        return (mu - mean) * inv_std, cache
 
     def encode_first(self, x):
         """x [1, 3, 1, H, W] -> mu [1, 16, 1, H/8, W/8]."""
