@@ -537,14 +537,19 @@ class Encoder3d(nn.Module):
 
 
 class EncoderEngine:
-    """Encoder3d + WanVAE_.conv1 + latent scaling on the sm_100a kernels, FIRST CHUNK only:
-    one pixel frame with an empty feature cache (vae_block3.py:136-150 with feat_cache[0] is None) —
-    every causal conv sees zero history and the downsample3d time_convs are skipped (vae.py:160-163).
-    That is exactly the server's first-frame re-encode (release_server.py:571-576)."""
+    """Encoder3d + WanVAE_.conv1 + latent scaling on the sm_100a kernels, streaming like the reference
+    (demo_utils/vae_block3.py:141-175 over wan/modules/vae.py:301-345): the first chunk is ONE pixel frame on
+    an empty cache (every causal conv sees zero history, the downsample3d time_convs are skipped and only
+    remember their input, vae.py:160-163), every later chunk is FOUR frames -> one latent frame (time_conv
+    (3,1,1) stride (2,1,1) over [last cached frame, chunk], vae.py:164-171).  As in the decoder engine each
+    causal conv owns a persistent input buffer whose two leading frames ARE its feature cache."""
+
+    MAX_CHUNK = 4          # pixel frames per later chunk
 
     def __init__(self, encoder: Encoder3d, conv1: nn.Module, mean: torch.Tensor, std: torch.Tensor):
         self.encoder, self.conv1_mod, self.mean, self.std = encoder, conv1, mean, std
         self._key = None
+        self.initialised = False
 
     def _prepare(self, dtype, device, H, W):
         e = self.encoder
@@ -571,37 +576,85 @@ class EncoderEngine:
                     wproj=m.proj.weight.data.reshape(C, C).to(device=device, dtype=dtype).contiguous(),
                     bproj=m.proj.bias.data.to(device=device, dtype=dtype).contiguous()))
             else:
-                self.blocks.append(dict(kind="down", C=m.dim, conv=pc(m.resample[1])))
+                d = dict(kind="down", mode=m.mode, C=m.dim, conv=pc(m.resample[1]))
+                if m.mode == "downsample3d":
+                    d["tconv"] = pc(m.time_conv)
+                self.blocks.append(d)
         self.g_head = g(e.head[0])
         self.head = pc(e.head[2])
         self.w_out = self.conv1_mod.weight.data.reshape(32, 32).to(device=device, dtype=dtype).contiguous()
         self.b_out = self.conv1_mod.bias.data.to(device=device, dtype=dtype).contiguous()
         self.mean_d = self.mean.to(device=device, dtype=dtype)
         self.inv_std_d = 1.0 / self.std.to(device=device, dtype=dtype)
-        # conv-input buffers [2 zero history frames + 1 frame]
-        z = lambda h, w, c: torch.zeros(3, h, w, c, dtype=dtype, device=device)  # noqa: E731
-        self.conv_in.buf = z(H, W, 64)
+        # conv-input buffers [2 history frames + up to t frames]; t halves at every downsample3d
+        z = lambda t, h, w, c: torch.zeros(2 + t, h, w, c, dtype=dtype, device=device)  # noqa: E731
+        t = self.MAX_CHUNK
+        self.conv_in.buf = z(t, H, W, 64)
         h, w = H, W
         for b in self.blocks:
             if b["kind"] == "res":
-                b["c1"].buf, b["c2"].buf = z(h, w, b["cin"]), z(h, w, b["cout"])
+                b["c1"].buf, b["c2"].buf = z(t, h, w, b["cin"]), z(t, h, w, b["cout"])
             elif b["kind"] == "down":
                 h, w = h // 2, w // 2
-        self.head.buf = z(h, w, self.head.cin)
+                if b["mode"] == "downsample3d":
+                    b["tcache"] = torch.zeros(1, h, w, b["C"], dtype=dtype, device=device)
+                    t = max(1, t // 2)
+        self.head.buf = z(t, h, w, self.head.cin)
         self._key = key
+        self.initialised = False
 
-    def _conv(self, c: _Conv, src=None, **kw):
+    # -- stream state ------------------------------------------------------------------------------
+    def _cache_tensors(self):
+        out = [self.conv_in.buf[:2]]
+        for b in self.blocks:
+            if b["kind"] == "res":
+                out += [b["c1"].buf[:2], b["c2"].buf[:2]]
+            elif b["kind"] == "down" and b["mode"] == "downsample3d":
+                out.append(b["tcache"])
+        out.append(self.head.buf[:2])
+        return out
+
+    def reset(self):
+        """Forget the stream: zero history frames (frames >= 2 of a buffer are rewritten before every use)."""
+        for c in self._cache_tensors():
+            c.zero_()
+        self.initialised = False
+
+    def export_cache(self) -> List[Optional[torch.Tensor]]:
+        """The reference's 55-slot list (24 used by the encoder); entries are this engine's own buffers."""
+        mine = self._cache_tensors()
+        return mine + [None] * (55 - len(mine))
+
+    def import_cache(self, cache):
+        if cache is None or all(c is None for c in cache):
+            self.reset()
+            return
+        mine = self._cache_tensors()
+        for src, dst in zip(cache, mine):
+            if src is None:
+                raise ValueError("partial VAE feature cache: pass back the list this encoder returned")
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src.reshape(dst.shape))
+        self.initialised = True
+
+    def _conv(self, c: _Conv, T, src=None, **kw):
         x = c.buf if src is None else src
-        ops.vae_conv(x, c.weight, c.bias, n=c.n, cout=c.cout, T=1, taps=c.taps,
+        ops.vae_conv(x, c.weight, c.bias, n=c.n, cout=c.cout, T=T, taps=c.taps,
                      tile=_tile_for(x.shape[1], x.shape[2]), **kw)
+        if src is None and c.taps[0] == 3:
+            tail = c.buf[T:T + 2]                  # roll: the last two input frames become the cache
+            c.buf[:2].copy_(tail.clone() if T < 2 else tail)
 
-    def encode_first(self, frame: torch.Tensor) -> torch.Tensor:
-        """frame [3, H, W] in [-1, 1] -> mu [16, H/8, W/8] (scaled latent), dtype of the engine."""
+    # -- one chunk ---------------------------------------------------------------------------------
+    def encode_chunk(self, frames: torch.Tensor, first: bool) -> torch.Tensor:
+        """frames [T, 3, H, W] in [-1, 1] (T == 1 when ``first``, else 4) -> mu [16, T', H/8, W/8] with
+        T' = 1: the scaled latent frame of this chunk."""
         dt, dev = self.dtype, self.device
-        H, W = self.H, self.W
-        new = lambda h, w, c: torch.empty(1, h, w, c, dtype=dt, device=dev)  # noqa: E731
+        T = frames.shape[0]
+        assert (T == 1) if first else (T == self.MAX_CHUNK), "chunks are 1 frame (first) or 4 frames"
+        new = lambda t, h, w, c: torch.empty(t, h, w, c, dtype=dt, device=dev)  # noqa: E731
         cin = self.conv_in
-        cin.buf[2, :, :, :3] = frame.to(dt).permute(1, 2, 0)
+        cin.buf[2:2 + T, :, :, :3] = frames.to(dt).permute(0, 2, 3, 1)
         blocks = self.blocks
 
         def next_norm(i):
@@ -610,43 +663,93 @@ class EncoderEngine:
                 return (nb["g1"], nb["c1"]) if nb["kind"] == "res" else (None, None)
             return self.g_head, self.head
 
-        h, w = H, W
-        x = new(h, w, cin.cout)
-        self._conv(cin, out_raw=x, out_norm=blocks[0]["c1"].buf[2:3], gamma=blocks[0]["g1"])
+        h, w = self.H, self.W
+        x = new(T, h, w, cin.cout)
+        self._conv(cin, T, out_raw=x, out_norm=blocks[0]["c1"].buf[2:2 + T], gamma=blocks[0]["g1"])
         for i, b in enumerate(blocks):
             if b["kind"] == "res":
                 res = x
                 if b["sc"] is not None:
-                    res = new(h, w, b["cout"])
-                    self._conv(b["sc"], src=x, out_raw=res)
-                self._conv(b["c1"], out_norm=b["c2"].buf[2:3], gamma=b["g2"])
+                    res = new(T, h, w, b["cout"])
+                    self._conv(b["sc"], T, src=x, out_raw=res)
+                self._conv(b["c1"], T, out_norm=b["c2"].buf[2:2 + T], gamma=b["g2"])
                 g, nxt = next_norm(i)
                 need_raw = nxt is not self.head
-                xo = new(h, w, b["cout"]) if need_raw else None
-                self._conv(b["c2"], residual=res, out_raw=xo,
-                           out_norm=nxt.buf[2:3] if g is not None else None, gamma=g)
+                xo = new(T, h, w, b["cout"]) if need_raw else None
+                self._conv(b["c2"], T, residual=res, out_raw=xo,
+                           out_norm=nxt.buf[2:2 + T] if g is not None else None, gamma=g)
                 x = xo
             elif b["kind"] == "attn":
                 x = _vae_attention(b, x)
                 nb = blocks[i + 1]
-                ops.vae_rmsnorm_silu(x, nb["g1"], nb["c1"].buf[2:3])
-            else:   # downsample: stride-2 conv behind ZeroPad2d((0,1,0,1)); first chunk skips time_conv
+                ops.vae_rmsnorm_silu(x, nb["g1"], nb["c1"].buf[2:2 + T])
+            else:   # Resample: stride-2 conv behind ZeroPad2d((0,1,0,1)) per frame (vae.py:84-92, :152-155)
                 g, nxt = next_norm(i)
-                xo = new(h // 2, w // 2, b["C"])
-                self._conv(b["conv"], src=x, out_raw=xo, out_norm=nxt.buf[2:3], gamma=g, sub2=True)
-                x, h, w = xo, h // 2, w // 2
-        y = new(h, w, self.head.cout)
-        self._conv(self.head, out_raw=y)
-        out = ops.gemm(y.view(h * w, self.head.cout), self.w_out, self.b_out)           # WanVAE_.conv1 (1x1x1)
+                C = b["C"]
+                h, w = h // 2, w // 2
+                if b["mode"] != "downsample3d" or first:
+                    xo = new(T, h, w, C)
+                    self._conv(b["conv"], T, src=x, out_raw=xo, out_norm=nxt.buf[2:2 + T], gamma=g, sub2=True)
+                    if b["mode"] == "downsample3d":
+                        b["tcache"].copy_(xo)                 # first chunk: remember, skip time_conv (:160-163)
+                    x = xo
+                else:
+                    # [last cached frame, T frames] -> time_conv (3,1,1), stride 2 in time: T/2 frames (:164-171)
+                    xin = new(T + 1, h, w, C)
+                    xin[:1].copy_(b["tcache"])
+                    self._conv(b["conv"], T, src=x, out_raw=xin[1:], sub2=True)
+                    b["tcache"].copy_(xin[T:T + 1])
+                    tc = b["tconv"]
+                    T2 = T // 2
+                    xo = new(T2, h, w, C)
+                    for j in range(T2):
+                        ops.vae_conv(xin[2 * j:2 * j + 3], tc.weight, tc.bias, n=tc.n, cout=tc.cout, T=1, taps=tc.taps,
+                                     tile=_tile_for(h, w), out_raw=xo[j:j + 1], out_norm=nxt.buf[2 + j:3 + j], gamma=g)
+                    x, T = xo, T2
+        y = new(T, h, w, self.head.cout)
+        self._conv(self.head, T, out_raw=y)
+        out = ops.gemm(y.view(T * h * w, self.head.cout), self.w_out, self.b_out)       # WanVAE_.conv1 (1x1x1)
         mu = out[:, :16]
         mu = (mu - self.mean_d.view(1, 16)) * self.inv_std_d.view(1, 16)               # vae_block3.py:168-172
-        return mu.t().reshape(16, h, w)
+        self.initialised = True
+        return mu.reshape(T, h, w, 16).permute(3, 0, 1, 2)
+
+    def encode_first(self, frame: torch.Tensor) -> torch.Tensor:
+        """frame [3, H, W] -> mu [16, H/8, W/8] on a fresh stream (the server's first-frame re-encode)."""
+        self.reset()
+        return self.encode_chunk(frame[None], first=True)[:, 0]
+
+    def encode(self, z: torch.Tensor, feat_cache, stream: bool = False):
+        """The wrapper loop of vae_block3.py:141-165: z [3, T, H, W] -> mu [16, T', H/8, W/8]."""
+        self.import_cache(feat_cache)
+        t = z.shape[1]
+        outs = []
+        offset = 1
+        for i in range(1 + (t - 1) // 4):
+            if i == 0 and not self.initialised:
+                outs.append(self.encode_chunk(z[:, :1].transpose(0, 1), first=True))
+            else:
+                start = i - 1
+                if stream:
+                    offset, start = 0, i
+                chunk = z[:, offset + 4 * start:offset + 4 * (start + 1)]
+                if chunk.shape[1] != self.MAX_CHUNK:
+                    raise ValueError(f"VAE encoder: chunk {i} has {chunk.shape[1]} frames (needs 4); pass 1 + 4k "
+                                     f"frames on a fresh cache or 4k frames with stream=True on a warm one")
+                o = self.encode_chunk(chunk.transpose(0, 1), first=False)
+                if i == 0 and stream:
+                    outs = [o]
+                else:
+                    outs.append(o)
+        return torch.cat(outs, dim=1) if len(outs) > 1 else outs[0]
 
 
 class VAEEncoderWrapper(nn.Module):
-    """demo_utils/vae_block3.py:116-175 for the first-chunk case: ``forward(z [1,3,1,H,W],
-    feat_cache (all None), stream=False) -> (mu [1,16,1,H/8,W/8], feat_cache)``.  Streaming
-    encodes of later chunks (v2v / webcam) are not implemented and raise."""
+    """demo_utils/vae_block3.py:116-175: ``forward(z [1, 3, T, H, W], feat_cache, stream=False) ->
+    (mu [1, 16, T', H/8, W/8], feat_cache)``.  Fresh cache (all None): T = 1 + 4k pixel frames -> 1 + k latent
+    frames (the server's first-frame re-encode, start frame and v2v uploads, release_server.py:531-538, :574,
+    :585); warm cache with ``stream=True``: T = 4k frames -> k latent frames (webcam blocks, :518-525).  The
+    returned cache entries are this implementation's channels-last buffers (opaque; pass them back)."""
 
     def __init__(self, vae=None):
         super().__init__()
@@ -665,12 +768,12 @@ class VAEEncoderWrapper(nn.Module):
         return super()._apply(fn, *a, **k)
 
     def forward(self, z: torch.Tensor, feat_cache, stream: bool = False):
-        if z.shape[0] != 1 or z.shape[2] != 1 or any(c is not None for c in feat_cache) or stream:
-            raise NotImplementedError("B200 VAE encoder: only the first chunk (one frame, empty cache) is "
-                                      "implemented; streaming / multi-chunk encode is a 'next' row")
+        if z.shape[0] != 1:
+            raise NotImplementedError("B200 VAE encoder: batch size 1 (as every call site of the reference)")
         if self._engine is None:
             self._engine = EncoderEngine(self.encoder, self.conv1, self.mean, self.std)
+        eng = self._engine
         dtype = z.dtype if z.dtype in (torch.float16, torch.bfloat16) else torch.float16
-        self._engine._prepare(dtype, z.device, z.shape[-2], z.shape[-1])
-        mu = self._engine.encode_first(z[0, :, 0])
-        return mu[None, :, None], feat_cache
+        eng._prepare(dtype, z.device, z.shape[-2], z.shape[-1])
+        mu = eng.encode(z[0], list(feat_cache), stream=stream)
+        return mu[None], eng.export_cache()

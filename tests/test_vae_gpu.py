@@ -114,3 +114,21 @@ def test_encoder_first_frame_vs_reference_golden(tag):
     assert mu.shape == ref.shape
     r = rel_l2(mu, ref)
     assert r < 2e-2, f"{tag}: rel_l2={r:.3e}"
+
+
+def test_encoder_streaming_vs_reference_golden():
+    """Streaming encode: 1 + 4 + 4 frames on a fresh cache, then 4 + 4 and 4 frames with
+    stream=True on the carried cache (release_server.py:518-538), fp16 engine vs the fp32 reference
+    VAEEncoderWrapper (tests/golden/make_vae_encoder_stream_goldens.py).  Tolerance: rel-L2 <= 2e-2."""
+    from realtime_video_b200.vae import VAEEncoderWrapper
+    g = load_npz("vae_encoder_stream.npz")
+    m = VAEEncoderWrapper()
+    m.load_state_dict(synthetic_vae_params(seed=0, encoder=True), strict=False)
+    m = m.to(device="cuda", dtype=torch.float16).eval()
+    cache = [None] * 55
+    with torch.no_grad():
+        for tag, stream in (("cold9_64x96", False), ("stream8_64x96", True), ("stream4_64x96", True)):
+            mu, cache = m(g[f"{tag}/x"].cuda().half(), cache, stream=stream)
+            assert mu.shape == g[f"{tag}/mu"].shape
+            r = rel_l2(mu, g[f"{tag}/mu"])
+            assert r < 2e-2, f"{tag}: rel_l2={r:.3e}"

@@ -83,3 +83,29 @@ def test_encoder_first_frame(g):
     assert mu.shape == g["enc64x96/mu"].shape
     r = rel_l2(mu, g["enc64x96/mu"])
     assert r < TOL, f"rel_l2={r:.3e}"
+
+
+def test_streaming_encoder_chunks(g):
+    """1 + 4 + 4 frames on a fresh cache, then 4 + 4 and 4 frames with stream=True on the carried cache — the two
+    ways the server calls the encoder (release_server.py:518-538) — against the reference's VAEEncoderWrapper."""
+    from realtime_video_b200.vae import VAEEncoderWrapper
+    gs = load_npz("vae_encoder_stream.npz")
+    m = VAEEncoderWrapper()
+    m.load_state_dict(synthetic_vae_params(seed=0, encoder=True), strict=False)
+    m = m.half().eval()
+    cache = [None] * 55
+    with torch.no_grad():
+        for tag, stream in (("cold9_64x96", False), ("stream8_64x96", True), ("stream4_64x96", True)):
+            mu, cache = m(gs[f"{tag}/x"].half(), cache, stream=stream)
+            assert mu.shape == gs[f"{tag}/mu"].shape and len(cache) == 55
+            r = rel_l2(mu, gs[f"{tag}/mu"])
+            assert r < TOL, f"{tag}: rel_l2={r:.3e}"
+        assert sum(c is not None for c in cache) == int(gs["n_cache_slots"][0])
+        # a fresh cache restarts the stream: same first latent frame as before
+        again, _ = m(gs["cold9_64x96/x"][:, :, :1].half(), [None] * 55)
+        assert rel_l2(again, gs["cold9_64x96/mu"][:, :, :1]) < TOL
+        # 1 + 4k + r frames: the trailing r < 4 frames are ignored like in the reference loop (1 + (t - 1) // 4 chunks)
+        seven, cache7 = m(gs["cold9_64x96/x"][:, :, :7].half(), [None] * 55)
+        assert seven.shape[2] == 2 and rel_l2(seven, gs["cold9_64x96/mu"][:, :, :2]) < TOL
+        with pytest.raises(ValueError, match="needs 4"):          # a ragged streaming chunk cannot be encoded
+            m(gs["stream8_64x96/x"][:, :, :6].half(), cache7, stream=True)
