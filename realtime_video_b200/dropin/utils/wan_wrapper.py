@@ -210,17 +210,31 @@ class WanDiffusionWrapper(nn.Module):
 
 
 class WanVAEWrapper(nn.Module):
-    """utils/wan_wrapper.py:58-118 — classic-path VAE.  ``self.model`` carries the reference's
-    ``decoder.*`` / ``conv2.*`` state-dict keys (the decoder half of WanVAE_); decode runs on the
-    sm_100a engine in the latent dtype (bf16 on the classic path, wan_wrapper.py:102-104)."""
+    """utils/wan_wrapper.py:58-118 — classic-path VAE.  ``self.model`` carries the reference's WanVAE_
+    state-dict keys (``encoder.*``, ``conv1.*``, ``conv2.*``, ``decoder.*``); decode and encode run on the
+    sm_100a engines in the tensor's 16-bit dtype (bf16 on the classic path, wan_wrapper.py:102-104)."""
 
     def __init__(self):
         super().__init__()
-        from realtime_video_b200.vae import MEAN, STD, VAEDecoderWrapper
+        from realtime_video_b200.vae import MEAN, STD, CausalConv3d, Encoder3d, VAEDecoderWrapper
+
+        class _WanVAEModel(VAEDecoderWrapper):
+            """decoder + conv2 (VAEDecoderWrapper) plus encoder + conv1: the module tree of WanVAE_ (vae.py:491-516)."""
+
+            def __init__(self):
+                super().__init__()
+                self.encoder = Encoder3d()
+                self.conv1 = CausalConv3d(32, 32, 1)
+
         self.mean = torch.tensor(MEAN, dtype=torch.float32)
         self.std = torch.tensor(STD, dtype=torch.float32)
-        self.model = VAEDecoderWrapper()
+        self.model = _WanVAEModel()
         self._cache = [None] * 55
+        self._enc_engine = None
+
+    def _apply(self, fn, *a, **k):     # .to() / .half() invalidate prepared weights
+        self._enc_engine = None
+        return super()._apply(fn, *a, **k)
 
     def decode_to_pixel(self, latent: torch.Tensor, use_cache: bool = False) -> torch.Tensor:
         """latent [B, F, 16, h, w] -> pixels [B, F', 3, H, W] fp32 in [-1, 1]
@@ -238,4 +252,13 @@ class WanVAEWrapper(nn.Module):
         return torch.stack(outs)
 
     def encode_to_latent(self, pixel: torch.Tensor) -> torch.Tensor:
-        raise NotImplementedError("VAE encoder is a 'next' row (SURVEY.md §8f.1)")
+        """pixel [B, 3, F, H, W] in [-1, 1], F = 1 + 4k -> latent [B, 1 + k, 16, H/8, W/8] fp32: per sample a fresh
+        stream of WanVAE_.encode (vae.py:491-517: chunks of 1, 4, 4, ... frames), wan_wrapper.py:80-96."""
+        from realtime_video_b200.vae import EncoderEngine
+        if self._enc_engine is None:
+            self._enc_engine = EncoderEngine(self.model.encoder, self.model.conv1, self.mean, self.std)
+        eng = self._enc_engine
+        dtype = pixel.dtype if pixel.dtype in (torch.float16, torch.bfloat16) else torch.float16
+        eng._prepare(dtype, pixel.device, pixel.shape[-2], pixel.shape[-1])
+        out = [eng.encode(u, [None] * 55, stream=False).float() for u in pixel]      # [16, T', h, w] each
+        return torch.stack(out, dim=0).permute(0, 2, 1, 3, 4)

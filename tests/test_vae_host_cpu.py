@@ -109,3 +109,22 @@ def test_streaming_encoder_chunks(g):
         assert seven.shape[2] == 2 and rel_l2(seven, gs["cold9_64x96/mu"][:, :, :2]) < TOL
         with pytest.raises(ValueError, match="needs 4"):          # a ragged streaming chunk cannot be encoded
             m(gs["stream8_64x96/x"][:, :, :6].half(), cache7, stream=True)
+
+
+def test_classic_wrapper_encode_to_latent(g):
+    """WanVAEWrapper.encode_to_latent (utils/wan_wrapper.py:80-96): per sample a fresh 1 + 4 + 4 stream; the
+    module tree accepts the reference's full WanVAE_ state dict (encoder.*, conv1.*, conv2.*, decoder.*)."""
+    import realtime_video_b200.dropin.utils.wan_wrapper as ww
+    gs = load_npz("vae_encoder_stream.npz")
+    w = ww.WanVAEWrapper()
+    sd = dict(synthetic_vae_params(seed=0, encoder=True))
+    sd.update(synthetic_vae_params(seed=0))
+    missing = w.model.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys and set(missing.missing_keys) <= {"mean", "std"}
+    w = w.half().eval()
+    x = gs["cold9_64x96/x"].half()
+    with torch.no_grad():
+        lat = w.encode_to_latent(torch.cat([x, x.flip(2)]))                 # batch of two different clips
+    assert lat.shape == (2, 3, 16, 8, 12) and lat.dtype == torch.float32
+    assert rel_l2(lat[0], gs["cold9_64x96/mu"][0].permute(1, 0, 2, 3)) < TOL
+    assert not torch.allclose(lat[0], lat[1])
