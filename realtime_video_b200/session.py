@@ -7,7 +7,7 @@ Per block (release_server.py:636-736):
     recompute_kv_cache  -> block >= 1: reset cache indices, one DiT pass at t=0 over the
                            kv_cache_num_frames clean context frames under the block-causal mask
     N denoise steps     -> DiT pass, flow->x0, re-noise with the session RNG (bf16 randn)
-    VAE decode          -> pixels [1, 12 (9 for block 0), 3, H, W] fp32 in [-1, 1]
+    VAE decode          -> pixels [1, 12, 3, H, W] fp32 in [-1, 1] (block 0: 9 frames decoded, the first 3 skipped)
 Webcam / v2v / prompt interpolation / start-frame are caller features outside the hot path.
 Once the context window slides, the reference re-encodes the oldest cached PIXEL frame into the first
 context latent (release_server.py:571-576): done here with the sm_100a VAE encoder
