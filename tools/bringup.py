@@ -238,8 +238,7 @@ def t_attnperf():
     torch.manual_seed(3)
     L, D, H = 4680, 5120, 40
     q = torch.randn(L, D, device=dev, dtype=torch.bfloat16)
-    import os
-    tag = f"parts={os.environ.get('KR_ATTN_PARTS', 'default')} packed={os.environ.get('KR_ATTN_PACKED', 'default')}"
+    tag = "attn_fwd_kernel"
     for Lkv in (9360, 4680, 512):
         k = torch.randn(Lkv, D, device=dev, dtype=torch.bfloat16)
         v = torch.randn(Lkv, D, device=dev, dtype=torch.bfloat16)
