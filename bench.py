@@ -442,7 +442,7 @@ def main():
         "metric": "frames_per_second_832x480_4step_t2v", "value": value, "unit": "frames/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
         "scaling": "strong" if sp_mode else "weak", "vs_baseline": (value / 11.0) if world == 1 else None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "model_dims": "Wan2.1-T2V-14B (40 layers, d 5120, ffn 13824, 40 heads)"
+        "config": {"workload": WORKLOAD, "dims": "Wan2.1-T2V-14B (40 layers, d 5120, ffn 13824, 40 heads)"
                    if args.layers == LAYERS else f"DEBUG {args.layers} layers",
                    "resolution": "832x480", "denoise_steps": 4, "kv_cache_num_frames": 3, "frames_per_step": 12,
                    "passes_per_step": "1-frame VAE encode + 1 KV recompute + 4 denoise DiT passes + VAE decode (fp16)",
