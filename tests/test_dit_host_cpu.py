@@ -22,8 +22,9 @@ def g():
 def cpu_ops(monkeypatch):
     import realtime_video_b200.dit as dit
     import realtime_video_b200.dropin.utils.wan_wrapper as ww
-    monkeypatch.setattr(dit, "ops", emu)
-    monkeypatch.setattr(ww, "ops", emu)
+    import realtime_video_b200.vae as vae
+    for mod in (dit, ww, vae):
+        monkeypatch.setattr(mod, "ops", emu)
 
 
 def build(g, num_layers=2, **kw):
@@ -121,13 +122,15 @@ def test_wrapper_flow_and_x0(g):
 
 def test_classic_inference_loop_host_logic_vs_reference():
     """CausalInferencePipeline.inference (2 blocks x (4 denoise + 1 context) passes with re-noising) on the CPU
-    against the latents of the UNMODIFIED reference pipeline (tests/golden/pipeline_small.npz): cache
-    allocation, per-block start offsets, timestep handling and the context pass are product code; the VAE is a
-    stub here (its parity is a GPU test).  fp32 on both sides: rel-L2 <= 1e-3."""
+    against the UNMODIFIED reference pipeline (tests/golden/pipeline_small.npz): cache allocation, per-block
+    start offsets, timestep handling, the context pass and WanVAEWrapper.decode_to_pixel are product code.
+    Latents: fp32 on both sides, rel-L2 <= 1e-3; video: the VAE engine stores fp16/bf16 activations, mean |d|
+    <= 5e-3 on pixels in [0, 1]."""
     import types
 
     from realtime_video_b200.dropin.pipeline import CausalInferencePipeline
-    from realtime_video_b200.dropin.utils.wan_wrapper import WanDiffusionWrapper
+    from realtime_video_b200.dropin.utils.wan_wrapper import WanDiffusionWrapper, WanVAEWrapper
+    from realtime_video_b200.factory import synthetic_vae_params
     g = load_npz("pipeline_small.npz")
     gd = load_npz("dit_small.npz")
     gen = WanDiffusionWrapper(model_name="synthetic", timestep_shift=5.0, is_causal=True,
@@ -135,25 +138,27 @@ def test_classic_inference_loop_host_logic_vs_reference():
     gen.model.load_state_dict(weights(gd, torch.float32), strict=False)
     gen = gen.float().eval()
 
-    class StubVAE(torch.nn.Module):
-        def decode_to_pixel(self, latent, use_cache=False):
-            b, f = latent.shape[:2]
-            return torch.zeros(b, f, 3, latent.shape[-2] * 8, latent.shape[-1] * 8)
+    vae = WanVAEWrapper()
+    vae.model.load_state_dict(synthetic_vae_params(seed=0), strict=False)
+    vae = vae.half().eval()
 
     ctx = g["ctx"].float()
     args = types.SimpleNamespace(denoising_step_list=[1000, 750, 500, 250], warp_denoising_step=True,
                                  num_frame_per_block=3, independent_first_frame=False, context_noise=0,
                                  model_kwargs={})
     pipe = CausalInferencePipeline(args, "cpu", generator=gen,
-                                   text_encoder=lambda text_prompts: {"prompt_embeds": ctx}, vae=StubVAE())
+                                   text_encoder=lambda text_prompts: {"prompt_embeds": ctx}, vae=vae)
     assert torch.allclose(pipe.denoising_step_list.float(), g["steps"].float())
     it = iter([g[f"draw{i}"] for i in range(6)])
     real = torch.randn_like
     torch.randn_like = lambda t, **kw: next(it).to(device=t.device, dtype=t.dtype)
     try:
-        _, latents = pipe.inference(g["noise"].float(), ["x"], return_latents=True)
+        video, latents = pipe.inference(g["noise"].float(), ["x"], return_latents=True)
     finally:
         torch.randn_like = real
     r = rel_l2(latents, g["latents"])
     assert r < 1e-3, f"latents rel_l2={r:.3e}"
+    assert video.shape == (1, 21, 3, 128, 192) and float(video.min()) >= 0.0 and float(video.max()) <= 1.0
+    mad = (video[..., ::2, ::2] - g["video_sub"]).abs().mean().item()
+    assert mad < 5e-3, f"video mean|d|={mad:.3e}"
     assert pipe.kv_cache1[0]["k"].shape[1] == 21 * 96
