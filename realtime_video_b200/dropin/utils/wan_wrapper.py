@@ -1,17 +1,14 @@
 """Drop-in for the reference's ``utils/wan_wrapper.py`` (the L2 boundary).
 
 Same class names, constructor arguments, attributes and call conventions as
-utils/wan_wrapper.py:20-323; the DiT underneath is ``realtime_video_b200.dit.CausalWanModel``
-(hand-written sm_100a kernels behind the C ABI).  ``WanTextEncoder`` (UMT5-XXL, once per prompt,
-off the per-frame path — SURVEY.md §2 row 13) is re-exported from the reference tree when that
-tree is importable further down ``sys.path``.
+utils/wan_wrapper.py:20-323; the DiT underneath is ``realtime_video_b200.dit.CausalWanModel``, the text
+encoder ``realtime_video_b200.t5.T5Encoder`` and the VAE ``realtime_video_b200.vae`` (hand-written sm_100a
+kernels behind the C ABI).
 """
 from __future__ import annotations
 
-import importlib.util
 import json
 import os
-import sys
 import types
 from typing import List, Optional
 
@@ -34,40 +31,74 @@ KNOWN_CONFIGS = {
 }
 
 
-def _reference_module(dotted: str, filename: str):
-    """Load ``filename`` of the reference tree from a later sys.path entry (ours shadows it)."""
-    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for base in sys.path:
-        cand = os.path.join(base or ".", filename)
-        if os.path.isfile(cand) and not os.path.abspath(cand).startswith(here):
-            spec = importlib.util.spec_from_file_location("_krea_ref_" + dotted.replace(".", "_"), cand)
-            mod = importlib.util.module_from_spec(spec)
-            spec.loader.exec_module(mod)
-            return mod
-    return None
+class _PromptTokenizer:
+    """The reference's HuggingfaceTokenizer(name, seq_len=512, clean='whitespace') (wan/modules/tokenizers.py:38-83):
+    ftfy.fix_text (when ftfy is installed) -> html.unescape twice -> collapse whitespace -> AutoTokenizer with
+    padding='max_length', truncation, max_length=seq_len -> (input_ids, attention_mask)."""
+
+    def __init__(self, name: str, seq_len: int = 512):
+        from transformers import AutoTokenizer
+        self.seq_len = seq_len
+        self.tokenizer = AutoTokenizer.from_pretrained(name)
+
+    @staticmethod
+    def clean(text: str) -> str:
+        import html
+        import re
+        try:
+            import ftfy
+            text = ftfy.fix_text(text)
+        except ImportError:       # not in this image; only matters for mojibake in the prompt
+            pass
+        text = html.unescape(html.unescape(text)).strip()
+        return re.sub(r"\s+", " ", text).strip()
+
+    def __call__(self, sequence, return_mask: bool = True, **_):
+        if isinstance(sequence, str):
+            sequence = [sequence]
+        enc = self.tokenizer([self.clean(u) for u in sequence], return_tensors="pt", padding="max_length",
+                             truncation=True, max_length=self.seq_len, add_special_tokens=True)
+        return (enc.input_ids, enc.attention_mask) if return_mask else enc.input_ids
 
 
-class _MissingReference(nn.Module):
-    _what = ""
+class WanTextEncoder(nn.Module):
+    """utils/wan_wrapper.py:20-56: UMT5-XXL encoder + tokenizer -> ``{"prompt_embeds": [B, 512, 4096]}`` with the
+    rows past each prompt's length zeroed.  The encoder underneath is ``realtime_video_b200.t5.T5Encoder`` (same
+    state-dict keys as the reference's ``umt5_xxl(encoder_only=True)``).  Extra keyword arguments (not in the
+    reference) allow construction without the checkpoint / tokenizer files: ``model_config`` (dims),
+    ``tokenizer`` (any callable ``(prompts, return_mask=True, add_special_tokens=True) -> (ids, mask)``),
+    ``device``.  As in the reference the module is built in fp32 and the caller casts it
+    (release_server.py:139-142 ``.to(dtype=torch.bfloat16)``)."""
 
-    def __init__(self, *a, **k):
+    def __init__(self, model_config: Optional[dict] = None, tokenizer=None, device=None) -> None:
         super().__init__()
-        raise ImportError(
-            f"{self._what} is not part of the B200 hot path (SURVEY.md §8f); put the reference "
-            f"checkout on sys.path after realtime_video_b200/dropin to use its implementation")
+        from realtime_video_b200.t5 import umt5_xxl_encoder
+        dev = device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu")
+        self.text_encoder = umt5_xxl_encoder(device=dev, dtype=torch.float32, **(model_config or {}))
+        ckpt = os.path.join(MODEL_FOLDER, "Wan2.1-T2V-1.3B", "models_t5_umt5-xxl-enc-bf16.safetensors")
+        if model_config is None and os.path.isfile(ckpt):
+            from safetensors.torch import load_file
+            self.text_encoder.load_state_dict(load_file(ckpt, device=str(dev)))
+        self.tokenizer = tokenizer
+        self._tokenizer_path = os.path.join(MODEL_FOLDER, "Wan2.1-T2V-1.3B", "google", "umt5-xxl/")
 
+    @property
+    def device(self):
+        return self.text_encoder.token_embedding.weight.device
 
-def _ref_class(name: str):
-    try:
-        mod = _reference_module("utils.wan_wrapper", os.path.join("utils", "wan_wrapper.py"))
-        if mod is not None:
-            return getattr(mod, name)
-    except Exception:  # noqa: BLE001  (reference import needs its own deps)
-        pass
-    return type(name, (_MissingReference,), {"_what": name})
-
-
-WanTextEncoder = _ref_class("WanTextEncoder")
+    def forward(self, text_prompts: List[str]) -> dict:
+        if self.tokenizer is None:
+            if not os.path.isdir(self._tokenizer_path):
+                raise FileNotFoundError(f"UMT5 tokenizer files not found under {self._tokenizer_path}; pass "
+                                        f"tokenizer=... to WanTextEncoder")
+            self.tokenizer = _PromptTokenizer(self._tokenizer_path, seq_len=512)
+        ids, mask = self.tokenizer(text_prompts, return_mask=True, add_special_tokens=True)
+        ids, mask = ids.to(self.device), mask.to(self.device)
+        seq_lens = mask.gt(0).sum(dim=1).long()
+        context = self.text_encoder(ids, mask)
+        for u, v in zip(context, seq_lens):
+            u[v:] = 0.0                              # set padding to 0.0 (wan_wrapper.py:52-53)
+        return {"prompt_embeds": context}
 
 
 class WanDiffusionWrapper(nn.Module):

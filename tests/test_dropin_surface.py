@@ -14,11 +14,14 @@ sys.path[:0] = [r"%(root)s", r"%(root)s/realtime_video_b200/dropin"]
 from pipeline import CausalInferencePipeline                                    # release_server.py:233
 from utils.wan_wrapper import WanDiffusionWrapper, WanTextEncoder, WanVAEWrapper  # release_server.py:28
 from utils.scheduler import FlowMatchScheduler                                  # release_server.py:556
-from demo_utils.vae_block3 import VAEDecoderWrapper                             # release_server.py:195
+from demo_utils.vae_block3 import VAEDecoderWrapper, VAEEncoderWrapper          # release_server.py:195, :189
 from demo_utils.vae import VAEDecoderWrapperSingle, ZERO_VAE_CACHE, ALL_INPUTS_NAMES
 from wan.modules.causal_model import CausalWanModel
 import realtime_video_b200.dit as dit, realtime_video_b200.vae as vae
 assert CausalWanModel is dit.CausalWanModel and VAEDecoderWrapper is vae.VAEDecoderWrapper
+assert VAEEncoderWrapper is vae.VAEEncoderWrapper
+import realtime_video_b200.t5 as t5
+assert isinstance(WanTextEncoder(model_config=dict(vocab=8, dim=64, dim_attn=64, dim_ffn=64, num_heads=1, num_layers=1, num_buckets=32), device='cpu').text_encoder, t5.T5Encoder)
 print("OK")
 """
 
