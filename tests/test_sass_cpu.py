@@ -1,0 +1,70 @@
+"""Static checks on the SASS of the built library (cuobjdump, no GPU needed): the hot kernels really are
+tcgen05 / TMA code for sm_100a, there is no legacy mma.sync tensor path, and the single-thread issue loops are
+emitted back to back — `lane == 0` guards make ptxas wrap every UTCHMMA / UTCBAR / UTMALDG in an ELECT + branch
+loop (13-15 instructions per MMA), `elect.sync` guards do not (DESIGN.md §4 'Issue threads')."""
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from realtime_video_b200 import _lib
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+
+
+@pytest.fixture(scope="module")
+def sass():
+    _lib.load()                      # builds the library if needed
+    out = subprocess.run(["cuobjdump", "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    funcs, name, body = {}, None, []
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            if name:
+                funcs[name] = body
+            name, body = m.group(1), []
+        elif name and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
+            body.append(line.split("*/", 1)[1].strip())
+    if name:
+        funcs[name] = body
+    return funcs
+
+
+def _ops(body):
+    return [(l.split()[1] if l.startswith("@") else l.split()[0]) for l in body if l]
+
+
+def test_compiled_for_sm_100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", str(_lib.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+@pytest.mark.parametrize("pattern,needs", [
+    ("gemm_tn_kernel", ("UTCHMMA", "UTMALDG", "UTCBAR", "LDTM")),
+    ("gemm2_tn_kernel", ("UTCHMMA.2CTA", "UTMALDG", "UTCBAR", "LDTM")),
+    ("attn_fwd_kernel", ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "MUFU.EX2")),
+    ("conv_igemm_kernel", ("UTCHMMA", "UTMALDG", "LDTM")),
+    ("conv_halo_kernel", ("UTCHMMA", "UTMALDG", "LDTM")),
+])
+def test_hot_kernels_are_tcgen05_and_tma(sass, pattern, needs):
+    hits = {k: v for k, v in sass.items() if pattern in k}
+    assert hits, f"no kernel matching {pattern}"
+    for name, body in hits.items():
+        ops = _ops(body)
+        for n in needs:
+            assert any(o.startswith(n) for o in ops), f"{name}: no {n}"
+
+
+def test_no_legacy_tensor_core_path(sass):
+    for name, body in sass.items():
+        assert not any(o.startswith(("HMMA", "IMMA", "HGMMA")) for o in _ops(body)), name
+
+
+def test_issue_threads_are_not_wrapped_in_elect_loops(sass):
+    for name, body in sass.items():
+        ops = _ops(body)
+        for i, o in enumerate(ops):
+            if o.startswith(("UTCHMMA", "UTCBAR", "UTMALDG")):
+                assert not any(p.startswith("ELECT") for p in ops[max(0, i - 2):i]), f"{name}: {o} behind an ELECT loop"
