@@ -4,7 +4,8 @@ rel-L2 7e-3 (tests/golden/make_t5_goldens.py); we require <= 2e-2 against both g
 
 The schedule only uses kernels that are validated elsewhere (kr_gemm, kr_rmsnorm, kr_softmax_rows), but this test
 itself was written after the round's GPU budget was spent and has not run on a B200 yet, hence non-strict xfail:
-a failure is reported as xfailed instead of stopping `pytest -x`, a pass shows up as xpassed."""
+a failure is reported as xfailed instead of stopping `pytest -x`, a pass shows up as xpassed.  The file name sorts last so that
+nothing runs after it in the same process."""
 import pytest
 import torch
 
