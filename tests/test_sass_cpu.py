@@ -68,3 +68,28 @@ def test_issue_threads_are_not_wrapped_in_elect_loops(sass):
         for i, o in enumerate(ops):
             if o.startswith(("UTCHMMA", "UTCBAR", "UTMALDG")):
                 assert not any(p.startswith("ELECT") for p in ops[max(0, i - 2):i]), f"{name}: {o} behind an ELECT loop"
+
+
+def test_register_and_stack_budget():
+    """Resource usage of the hot kernels (cuobjdump --dump-resource-usage): the GEMM and conv kernels keep their
+    whole epilogue in registers (no stack), the attention softmax threads stay within the 168 registers that
+    384 threads per SM allow with at most a few spill slots."""
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", str(_lib.LIB_PATH)], capture_output=True, text=True,
+                         check=True).stdout
+    usage = {}
+    name = None
+    for line in out.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+        elif name and "REG:" in line:
+            usage[name] = (int(re.search(r"REG:(\d+)", line).group(1)), int(re.search(r"STACK:(\d+)", line).group(1)))
+            name = None
+    assert usage
+    for fn, (reg, stack) in usage.items():
+        head_conv = "conv_igemm_kernelILi96ELi16E" in fn      # 96 -> 3 head: runtime channel loop over a 16-entry array
+        if any(k in fn for k in ("gemm_tn_kernel", "gemm2_tn_kernel", "conv_igemm_kernel", "conv_halo_kernel")) \
+                and not head_conv:
+            assert stack == 0, (fn, reg, stack)
+        if "attn_fwd_kernel" in fn:
+            assert reg <= 168 and stack <= 64, (fn, reg, stack)
