@@ -403,6 +403,7 @@ def main():
     # launches, plus the split between the two kernels behind kr_gemm (CTA-pair / single-CTA)
     gem = prof.get("gemm", {"flops": 0.0, "ms": 0.0, "n": 0})
     att = prof.get("attention", {"flops": 0.0, "ms": 0.0, "n": 0})
+    vcv = prof.get("vae_conv", {"flops": 0.0, "ms": 0.0, "n": 0})
     achieved = gem["flops"] / (gem["ms"] * 1e-3) / 1e12 if gem["ms"] > 0 else None
     traffic_db = {}
     tp = ROOT / "profiles" / "r01_gemm_traffic.json"
@@ -430,7 +431,11 @@ def main():
                 "by_kernel": by_kernel,
                 "attention": {"achieved": att["flops"] / (att["ms"] * 1e-3) / 1e12 if att["ms"] > 0 else None,
                               "unit": "TFLOP/s", "launches_timed": att["n"],
-                              "share_of_step": att["ms"] / ms if ms > 0 else None}}
+                              "share_of_step": att["ms"] / ms if ms > 0 else None},
+                # VAE (decoder + first-frame encoder) implicit-GEMM convs: 2*taps*Cin*Cout*pixels per launch
+                "vae_conv": {"achieved": vcv["flops"] / (vcv["ms"] * 1e-3) / 1e12 if vcv["ms"] > 0 else None,
+                             "unit": "TFLOP/s", "launches_timed": vcv["n"],
+                             "share_of_step": vcv["ms"] / ms if ms > 0 else None}}
     block_tflop = (4 * LAYERS * layer_flops(LQ, LKV) + LAYERS * layer_flops(LQ, LQ)) / 1e12 * (args.layers / LAYERS)
     cpu = None
     if not args.no_cpu_baseline:
