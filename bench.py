@@ -281,12 +281,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from realtime_video_b200 import factory, ops
-    from realtime_video_b200.session import GenerateParams, GenerationSession
+    import harness
+    from harness import GenerateParams, GenerationSession
     K, W = args.steps, args.warmup
     transformer = factory.synthetic_transformer("14B", device=dev, num_layers=args.layers, seed=0)
     vae = factory.synthetic_vae_decoder(device=dev)
     vae_enc = factory.synthetic_vae_encoder(device=dev)
-    models = factory.build_models(transformer, vae_decoder=vae, device=dev, vae_encoder=vae_enc)
+    models = harness.build_models(transformer, vae_decoder=vae, device=dev, vae_encoder=vae_enc)
     pe = factory.synthetic_prompt_embeds(device=dev)
 
     def barrier():

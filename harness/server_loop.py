@@ -1,18 +1,20 @@
-"""Block driver for the hot path — the text-to-video subset of the reference's
-``GenerationSession`` (release_server.py:344-736) restated over the drop-in classes, so that
-``bench.py`` / ``smoke()`` / the tests can run the server's per-block sequence on a box where the
-reference checkout (and its FastAPI / omegaconf dependencies) does not exist.
+"""TEST / BENCH INFRASTRUCTURE — stand-in for the text-to-video path of the reference's ``GenerationSession``
+(release_server.py:344-736) on boxes where the reference checkout (and its FastAPI / omegaconf dependencies)
+does not exist: ``bench.py``, ``smoke()`` and the ``-m gpu`` tests drive the server's per-block sequence
+through it.  In a real deployment the reference's OWN ``GenerationSession`` runs unmodified on the drop-in
+classes; ``tests/test_reference_callers_cpu.py`` executes exactly that (unmodified release_server.py) and
+asserts bit-equality with this stand-in block by block, and ``tests/golden/server_loop_small.npz`` holds the
+same loop executed by the reference modules alone.
 
 Per block (release_server.py:636-736):
-    recompute_kv_cache  -> block >= 1: reset cache indices, one DiT pass at t=0 over the
+    recompute_kv_cache  -> block >= 1: re-initialise the cache, one DiT pass at t=0 over the
                            kv_cache_num_frames clean context frames under the block-causal mask
     N denoise steps     -> DiT pass, flow->x0, re-noise with the session RNG (bf16 randn)
     VAE decode          -> pixels [1, 12, 3, H, W] fp32 in [-1, 1] (block 0: 9 frames decoded, the first 3 skipped)
 Webcam / v2v / prompt interpolation / start-frame are caller features outside the hot path.
 Once the context window slides, the reference re-encodes the oldest cached PIXEL frame into the first
-context latent (release_server.py:571-576): done here with the sm_100a VAE encoder
-(``realtime_video_b200.vae.VAEEncoderWrapper``) when ``models.vae_encoder`` is given; without an encoder
-(or with ``keep_first_frame=True``) the first latent frame is kept (release_server.py:566-570).
+context latent (release_server.py:571-576; at 832x480 its bicubic resize to 480x832 is the identity): done
+with ``models.vae_encoder``; with ``keep_first_frame=True`` the first latent frame is kept (:566-570).
 """
 from __future__ import annotations
 
@@ -22,7 +24,7 @@ from typing import Optional
 
 import torch
 
-from .dropin.utils.scheduler import FlowMatchScheduler
+from realtime_video_b200.wan_wrapper import FlowMatchScheduler
 
 
 @dataclass

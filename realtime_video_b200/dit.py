@@ -175,7 +175,6 @@ class CausalWanModel(nn.Module):
         self.freqs = torch.polar(torch.ones_like(ang), ang)
         self._rope_angles = ang
         self._rope_table: Optional[torch.Tensor] = None      # device float32 (cos, sin)
-        self._ctx_cache = None                                # (key, embedded text)
         self.sp = None          # optional parallel.SequenceParallel (single-stream multi-GPU mode)
         self.init_weights()
         self.gradient_checkpointing = False
@@ -219,21 +218,16 @@ class CausalWanModel(nn.Module):
 
     # ----------------------------------------------------------------------------------------
     def _embed_text(self, context: torch.Tensor) -> torch.Tensor:
-        """text_embedding over the zero-padded prompt (causal_model.py:895-902).  The reference
-        recomputes it on every forward; the result only depends on the prompt tensor, so it is
-        kept per (storage, version) — bit-identical output."""
-        key = (context.data_ptr(), context._version, tuple(context.shape), context.dtype)
-        if self._ctx_cache is not None and self._ctx_cache[0] == key:
-            return self._ctx_cache[1]
+        """text_embedding over the zero-padded prompt (causal_model.py:895-902).  Its only consumer is the
+        cross-attention K/V projection, so ``forward_tokens`` calls it only on passes where some block's
+        ``crossattn_cache`` is not initialised (the reference recomputes it on every forward and discards it)."""
         te = self.text_embedding
         ctx = context
         if ctx.shape[0] < self.text_len:
             ctx = torch.cat([ctx, ctx.new_zeros(self.text_len - ctx.shape[0], ctx.shape[1])])
         ctx = ctx.to(te[0].weight.dtype).contiguous()
         h = ops.gemm(ctx, te[0].weight, te[0].bias, epilogue=ops.EPI_BIAS_GELU)
-        out = ops.gemm(h, te[2].weight, te[2].bias)
-        self._ctx_cache = (key, out)
-        return out
+        return ops.gemm(h, te[2].weight, te[2].bias)
 
     def _self_attention(self, blk: CausalWanAttentionBlock, h, grid, kv_cache, current_start, mask):
         """causal_model.py:218-397: projections, q/k RMSNorm, RoPE, cache write, attention.
@@ -399,7 +393,8 @@ class CausalWanModel(nn.Module):
         te, tp = self.time_embedding, self.time_projection
         e = ops.gemm(ops.activation(ops.gemm(emb, te[0].weight, te[0].bias), "silu"), te[2].weight, te[2].bias)
         e0 = ops.gemm(ops.activation(e, "silu"), tp[1].weight, tp[1].bias).view(Fr, 6, self.dim)
-        ctx = self._embed_text(context)
+        need_text = crossattn_cache is None or not all(c["is_init"] for c in crossattn_cache)
+        ctx = self._embed_text(context) if need_text else None
         mask = self.block_mask
         for i, blk in enumerate(self.blocks):
             xs = self._block(blk, xs, e0, grid, ctx, kv_cache[i],

@@ -4,13 +4,9 @@ build or GPU boxes): the reference's init (xavier / N(0,.02)) wi
 (causal_model.py:1173) and a zero head makes every output identically zero."""
 from __future__ import annotations
 
-import types
-
 import torch
 
-from .dropin.pipeline.causal_inference import CausalInferencePipeline
-from .dropin.utils.wan_wrapper import KNOWN_CONFIGS, WanDiffusionWrapper
-from .session import Models
+from .wan_wrapper import KNOWN_CONFIGS, WanDiffusionWrapper
 
 
 def synthetic_transformer(size: str = "14B", device="cuda", dtype=torch.bfloat16, seed: int = 0,
@@ -39,21 +35,6 @@ def synthetic_prompt_embeds(device="cuda", text_dim: int = 4096, tokens: int = 6
     e = torch.randn(1, 512, text_dim, generator=g)
     e[:, tokens:] = 0
     return e.to(device=device, dtype=torch.bfloat16)
-
-
-def pipeline_args(denoising_step_list=(1000, 750, 500, 250), num_frame_per_block: int = 3):
-    """configs/default_config.yaml + self_forcing_server_14b.yaml values the pipeline reads."""
-    return types.SimpleNamespace(denoising_step_list=list(denoising_step_list), warp_denoising_step=True,
-                                 num_frame_per_block=num_frame_per_block, independent_first_frame=False,
-                                 context_noise=0, model_kwargs={})
-
-
-def build_models(transformer: WanDiffusionWrapper, vae_decoder=None, text_encoder=None, device="cuda",
-                 vae_encoder=None) -> Models:
-    pipe = CausalInferencePipeline(pipeline_args(), device=device, generator=transformer,
-                                   text_encoder=text_encoder if text_encoder is not None else object(),
-                                   vae=vae_decoder if vae_decoder is not None else object())
-    return Models(text_encoder, transformer, pipe, vae_encoder, vae_decoder)
 
 
 def synthetic_vae_params(seed: int = 0, dim: int = 96, z_dim: int = 16, encoder: bool = False):

@@ -26,8 +26,12 @@ def _count(n: int = 1) -> None:
     launch_count += n
 
 
+_launch_device = None      # device of the operands of the op being issued (set by _req)
+
+
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """The caller's current stream ON THE OPERANDS' DEVICE (not the process-wide current device)."""
+    return torch.cuda.current_stream(_launch_device).cuda_stream
 
 
 # Optional per-kernel timing (bench.py roofline): CUDA events recorded on the launching stream
@@ -81,8 +85,15 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def _req(t: torch.Tensor, name: str, dtype=None) -> None:
+    global _launch_device
     if not t.is_cuda:
         raise _lib.KreaB200Error(f"{name} must be a CUDA tensor (no CPU fallback in the product path)")
+    if t.device.index != torch.cuda.current_device():
+        # kernels and TMA descriptors are issued on the CURRENT device; a model living on another GPU must be
+        # driven under torch.cuda.device(...) like the reference server does (release_server.py:741)
+        raise _lib.KreaB200Error(f"{name} lives on {t.device} but the current device is cuda:"
+                                 f"{torch.cuda.current_device()}; wrap the call in torch.cuda.device({t.device.index})")
+    _launch_device = t.device
     if dtype is not None and t.dtype != dtype:
         raise _lib.KreaB200Error(f"{name} must be {dtype}, got {t.dtype}")
 

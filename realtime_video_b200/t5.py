@@ -109,6 +109,9 @@ class T5Encoder(nn.Module):
     def _encode_one(self, ids: torch.Tensor, mask: Optional[torch.Tensor]) -> torch.Tensor:
         """ids [L], mask [L] or None -> [L, dim]."""
         dt = self.token_embedding.weight.dtype
+        if ids.is_cuda and dt not in (torch.bfloat16, torch.float16):
+            raise TypeError(f"T5Encoder runs on 16-bit weights (the server casts it: release_server.py:141 "
+                            f"text_encoder.to(dtype=torch.bfloat16)); got {dt}")
         L = ids.shape[0]
         n, hd, da = self.num_heads, self.dim_attn // self.num_heads, self.dim_attn
         x = self.token_embedding.weight[ids].contiguous()                     # [L, dim]

@@ -777,3 +777,18 @@ class VAEEncoderWrapper(nn.Module):
         eng._prepare(dtype, z.device, z.shape[-2], z.shape[-1])
         mu = eng.encode(z[0], list(feat_cache), stream=stream)
         return mu[None], eng.export_cache()
+
+
+def __getattr__(name: str):
+    """``demo_utils.vae`` re-exports ``ZERO_VAE_CACHE`` / ``ALL_INPUTS_NAMES`` (demo_utils/vae.py:6, used by
+    demo_utils/vae_torch2trt.py:2-5).  When this module is served under that name (realtime_video_b200.dropin) the
+    two constants come from the reference's own ``demo_utils/constant.py`` — ``VAEDecoderWrapperSingle`` accepts its
+    ``[1, C, 2, H, W]`` cache tensors."""
+    if name in ("ZERO_VAE_CACHE", "ALL_INPUTS_NAMES"):
+        try:
+            import demo_utils.constant as c      # the reference checkout
+        except ImportError as e:
+            raise AttributeError(f"{name} lives in the reference's demo_utils/constant.py, which is not importable "
+                                 f"here ({e})") from None
+        return getattr(c, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

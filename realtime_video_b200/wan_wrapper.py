@@ -1,9 +1,14 @@
-"""Drop-in for the reference's ``utils/wan_wrapper.py`` (the L2 boundary).
+"""The reference's ``utils/wan_wrapper.py`` on the B200 kernels (the L2 boundary).
 
 Same class names, constructor arguments, attributes and call conventions as
 utils/wan_wrapper.py:20-323; the DiT underneath is ``realtime_video_b200.dit.CausalWanModel``, the text
 encoder ``realtime_video_b200.t5.T5Encoder`` and the VAE ``realtime_video_b200.vae`` (hand-written sm_100a
-kernels behind the C ABI).
+kernels behind the C ABI).  ``realtime_video_b200.dropin.install()`` serves this module under the name
+``utils.wan_wrapper``, so the reference's own ``pipeline/causal_inference.py`` and ``release_server.py``
+construct and call these classes unchanged.
+
+Checkpoints: like the reference, the constructors load ``MODEL_FOLDER/...`` files and RAISE when they are
+missing; pass ``model_config=...`` (dims for a synthetic / caller-loaded model) to build without files.
 """
 from __future__ import annotations
 
@@ -17,7 +22,12 @@ from torch import nn
 
 from realtime_video_b200 import ops
 from realtime_video_b200.dit import CausalWanModel
-from realtime_video_b200.dropin.utils.scheduler import FlowMatchScheduler, SchedulerInterface
+
+try:   # dropped into the reference: its own pure-torch scheduler (utils/scheduler.py:5-194)
+    from utils.scheduler import FlowMatchScheduler, SchedulerInterface  # type: ignore
+except ImportError:   # stand-alone (bench / tests on a box without the reference checkout)
+    from realtime_video_b200.flow_match import FlowMatchSchedule as FlowMatchScheduler
+    SchedulerInterface = None
 
 try:  # reference settings.py:1-5
     from settings import MODEL_FOLDER  # type: ignore
@@ -74,9 +84,12 @@ class WanTextEncoder(nn.Module):
         super().__init__()
         from realtime_video_b200.t5 import umt5_xxl_encoder
         dev = device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu")
-        self.text_encoder = umt5_xxl_encoder(device=dev, dtype=torch.float32, **(model_config or {}))
         ckpt = os.path.join(MODEL_FOLDER, "Wan2.1-T2V-1.3B", "models_t5_umt5-xxl-enc-bf16.safetensors")
-        if model_config is None and os.path.isfile(ckpt):
+        if model_config is None and not os.path.isfile(ckpt):
+            # reference :30-33 loads unconditionally and fails without the file
+            raise FileNotFoundError(f"{ckpt} not found; pass model_config=... to build without a checkpoint")
+        self.text_encoder = umt5_xxl_encoder(device=dev, dtype=torch.float32, **(model_config or {}))
+        if model_config is None:
             from safetensors.torch import load_file
             self.text_encoder.load_state_dict(load_file(ckpt, device=str(dev)))
         self.tokenizer = tokenizer
@@ -112,6 +125,7 @@ class WanDiffusionWrapper(nn.Module):
         if not is_causal:
             raise NotImplementedError("the bidirectional WanModel is outside the hot path (SURVEY.md §2 row 2)")
         cfg = dict(model_config) if model_config else self._find_config(model_name)
+        shards = [] if (model_config is not None or meta_init) else self._checkpoint_shards(model_name)
         cfg.update(local_attn_size=local_attn_size, sink_size=sink_size)
         ctx = torch.device("meta") if meta_init else (torch.device(device) if device is not None else None)
         prev = torch.get_default_dtype()
@@ -125,7 +139,8 @@ class WanDiffusionWrapper(nn.Module):
                 self.model = CausalWanModel(**cfg)
         finally:
             torch.set_default_dtype(prev)
-        self._maybe_load_pretrained(model_name, meta_init)
+        if shards:
+            self._load_pretrained(shards)
         self.model.eval()
         self.uniform_timestep = not is_causal
         self.scheduler = FlowMatchScheduler(shift=timestep_shift, sigma_min=0.0, extra_one_step=True)
@@ -153,27 +168,38 @@ class WanDiffusionWrapper(nn.Module):
         raise FileNotFoundError(f"no config.json under {os.path.join(MODEL_FOLDER, model_name)} and "
                                 f"'{model_name}' names no known Wan 2.1 size")
 
-    def _maybe_load_pretrained(self, model_name: str, meta_init: bool) -> None:
+    @staticmethod
+    def _checkpoint_shards(model_name: str) -> list:
+        """``CausalWanModel.from_pretrained(MODEL_FOLDER/model_name)`` (:135-141) reads the diffusers-format
+        safetensors shards and fails without them; checked before the model is built."""
         folder = os.path.join(MODEL_FOLDER, model_name)
-        if meta_init or not os.path.isdir(folder):
-            return
-        files = sorted(f for f in os.listdir(folder)
-                       if f.startswith("diffusion_pytorch_model") and f.endswith(".safetensors"))
+        files = sorted(os.path.join(folder, f) for f in os.listdir(folder)
+                       if f.startswith("diffusion_pytorch_model") and f.endswith(".safetensors")) \
+            if os.path.isdir(folder) else []
         if not files:
-            return
+            raise FileNotFoundError(f"no diffusion_pytorch_model*.safetensors under {folder}; pass "
+                                    f"model_config=... to build the model without a checkpoint")
+        return files
+
+    def _load_pretrained(self, shards: list) -> None:
+        """strict load; the server overwrites these weights right afterwards with its self-forcing
+        checkpoint (release_server.py:160-171)."""
         from safetensors.torch import load_file
         sd = {}
-        for f in files:
-            sd.update(load_file(os.path.join(folder, f)))
-        self.model.load_state_dict(sd, strict=False)
+        for f in shards:
+            sd.update(load_file(f))
+        self.model.load_state_dict(sd, strict=True)
 
     # -- utils/wan_wrapper.py:181-228 ---------------------------------------------------------
     def _sigma_table(self, device):
-        key = (device, self.scheduler.sigmas.data_ptr(), self.scheduler.timesteps.data_ptr())
-        if self._sched_dev is None or self._sched_dev[0] != key:
-            self._sched_dev = (key, self.scheduler.sigmas.double().to(device),
-                               self.scheduler.timesteps.double().to(device))
-        return self._sched_dev[1], self._sched_dev[2]
+        """float64 device copies of the scheduler's tables, rebuilt whenever the scheduler swaps its tensors
+        (set_timesteps / ``.to``).  The source tensors are held and compared by identity, so a recycled
+        address can never serve stale sigmas."""
+        sig, ts = self.scheduler.sigmas, self.scheduler.timesteps
+        c = self._sched_dev
+        if c is None or c[0] is not sig or c[1] is not ts or c[2] != device:
+            c = self._sched_dev = (sig, ts, device, sig.double().to(device), ts.double().to(device))
+        return c[3], c[4]
 
     def _sigma_of(self, timestep: torch.Tensor, device) -> torch.Tensor:
         sigmas, timesteps = self._sigma_table(device)
@@ -226,11 +252,13 @@ class WanDiffusionWrapper(nn.Module):
                     c["global_end_index"], c["local_end_index"] = cb["global_end_index"], cb["local_end_index"]
         return torch.stack(flows), torch.stack(x0s)
 
-    def get_scheduler(self) -> SchedulerInterface:
-        """(:303-315) binds the interface's conversion helpers onto the scheduler instance."""
+    def get_scheduler(self):
+        """(:303-315) binds the reference SchedulerInterface's conversion helpers onto the scheduler instance
+        (training-side helpers; absent when the package runs without the reference checkout)."""
         s = self.scheduler
-        for name in ("convert_x0_to_noise", "convert_noise_to_x0", "convert_velocity_to_x0"):
-            setattr(s, name, types.MethodType(getattr(SchedulerInterface, name), s))
+        if SchedulerInterface is not None:
+            for name in ("convert_x0_to_noise", "convert_noise_to_x0", "convert_velocity_to_x0"):
+                setattr(s, name, types.MethodType(getattr(SchedulerInterface, name), s))
         return s
 
     def post_init(self):
@@ -245,7 +273,9 @@ class WanVAEWrapper(nn.Module):
     state-dict keys (``encoder.*``, ``conv1.*``, ``conv2.*``, ``decoder.*``); decode and encode run on the
     sm_100a engines in the tensor's 16-bit dtype (bf16 on the classic path, wan_wrapper.py:102-104)."""
 
-    def __init__(self):
+    def __init__(self, load_pretrained: bool = True):
+        """``load_pretrained=False`` (not in the reference) builds the module tree without
+        ``MODEL_FOLDER/Wan2.1-T2V-1.3B/Wan2.1_VAE.pth`` for synthetic / caller-loaded weights."""
         super().__init__()
         from realtime_video_b200.vae import MEAN, STD, CausalConv3d, Encoder3d, VAEDecoderWrapper
 
@@ -260,6 +290,13 @@ class WanVAEWrapper(nn.Module):
         self.mean = torch.tensor(MEAN, dtype=torch.float32)
         self.std = torch.tensor(STD, dtype=torch.float32)
         self.model = _WanVAEModel()
+        if load_pretrained:               # reference :73-77 (_video_vae(pretrained_path=...)): fails without the file
+            vae_path = os.path.join(MODEL_FOLDER, "Wan2.1-T2V-1.3B", "Wan2.1_VAE.pth")
+            if not os.path.isfile(vae_path):
+                raise FileNotFoundError(f"{vae_path} not found; WanVAEWrapper(load_pretrained=False) builds the "
+                                        f"module without a checkpoint")
+            self.model.load_state_dict(torch.load(vae_path, map_location="cpu"), assign=True)
+        self.model.eval().requires_grad_(False)
         self._cache = [None] * 55
         self._enc_engine = None
 

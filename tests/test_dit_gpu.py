@@ -110,7 +110,7 @@ def test_eviction_branch(g):
 
 
 def test_wrapper_flow_and_x0(g):
-    from realtime_video_b200.dropin.utils.wan_wrapper import WanDiffusionWrapper
+    from realtime_video_b200.wan_wrapper import WanDiffusionWrapper
     w = WanDiffusionWrapper(model_name="synthetic", timestep_shift=5.0, is_causal=True,
                             model_config=dict(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=128))
     w.model.load_state_dict(weights(g, torch.bfloat16), strict=False)

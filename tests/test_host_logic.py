@@ -35,8 +35,8 @@ def test_vae_state_dict_contract():
 
 
 def test_scheduler_matches_reference_tables():
-    from realtime_video_b200.dropin.utils.scheduler import FlowMatchScheduler
-    from realtime_video_b200.session import get_denoising_schedule
+    from realtime_video_b200.flow_match import FlowMatchSchedule as FlowMatchScheduler
+    from harness import get_denoising_schedule
     g = load_npz("dit_small.npz")
     s = FlowMatchScheduler(shift=5.0, sigma_min=0.0, extra_one_step=True)
     s.set_timesteps(1000, training=True)
@@ -50,10 +50,11 @@ def test_scheduler_matches_reference_tables():
 
 
 def test_pipeline_cache_allocation_and_reset():
+    import harness
     from realtime_video_b200 import factory
     w = factory.synthetic_transformer("14B", device="cpu", dtype=torch.float32, num_layers=2, dim=256,
                                       ffn_dim=512, num_heads=2, text_dim=128)
-    models = factory.build_models(w, device="cpu")
+    models = harness.build_models(w, device="cpu")
     p = models.pipeline
     assert p.frame_seq_length == 1560 and p.num_frame_per_block == 3
     p.local_attn_size = 6

@@ -17,8 +17,8 @@ pytestmark = pytest.mark.gpu
 
 
 def test_classic_inference_loop_vs_reference():
-    from realtime_video_b200.dropin.pipeline import CausalInferencePipeline
-    from realtime_video_b200.dropin.utils.wan_wrapper import WanDiffusionWrapper, WanVAEWrapper
+    from harness import PipelineState as CausalInferencePipeline
+    from realtime_video_b200.wan_wrapper import WanDiffusionWrapper, WanVAEWrapper
     from realtime_video_b200.factory import synthetic_vae_params
     g = load_npz("pipeline_small.npz")
     gd = load_npz("dit_small.npz")
@@ -26,7 +26,7 @@ def test_classic_inference_loop_vs_reference():
                               model_config=dict(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=128))
     gen.model.load_state_dict(weights(gd, torch.bfloat16), strict=False)
     gen = gen.to(device="cuda", dtype=torch.bfloat16).eval()
-    vae = WanVAEWrapper()
+    vae = WanVAEWrapper(load_pretrained=False)
     vae.model.load_state_dict(synthetic_vae_params(seed=0), strict=False)
     vae = vae.to(device="cuda", dtype=torch.bfloat16).eval()
     ctx = g["ctx"].cuda().to(torch.bfloat16)
@@ -35,6 +35,7 @@ def test_classic_inference_loop_vs_reference():
                                  model_kwargs={})
     pipe = CausalInferencePipeline(args, "cuda", generator=gen,
                                    text_encoder=lambda text_prompts: {"prompt_embeds": ctx}, vae=vae)
+    pipe.frame_seq_length = 96          # (H/16)*(W/16); the reference's literal 1560 is 832x480
     assert torch.allclose(pipe.denoising_step_list.float(), g["steps"].float())
     draws = [g[f"draw{i}"] for i in range(6)]
     it = iter(draws)
@@ -50,5 +51,4 @@ def test_classic_inference_loop_vs_reference():
     assert r < 4e-2, f"latents rel_l2={r:.3e}"
     mad = (video[..., ::2, ::2].cpu() - g["video_sub"]).abs().mean().item()
     assert mad < 2e-2, f"video mean|d|={mad:.3e}"
-    # the 21-frame KV cache default of the classic path (32760 tokens at 1560 tokens/frame)
-    assert pipe.kv_cache1[0]["k"].shape[1] == 21 * 96
+    assert pipe.kv_cache1[0]["k"].shape[1] == 32760     # the classic path's literal cache size (:289)

@@ -1,8 +1,8 @@
-"""The block driver (realtime_video_b200/session.py = the text-to-video subset of release_server.py:344-736) end
+"""The block driver stand-in (harness/server_loop.py = the text-to-video subset of release_server.py:344-736) end
 to end on the CPU at a tiny geometry, kernels replaced by the fp32 stand-ins of tests/cpu_ops_emulation.py:
 KV-cache recompute over the clean context frames, 4 denoise passes with re-noising, VAE decode, the sliding
-context window and the first-frame re-encode through the VAE encoder.  There is no reference fixture for the
-server loop (it cannot be imported without FastAPI / CUDA), so this checks the loop's invariants."""
+context window and the first-frame re-encode through the VAE encoder: the loop's invariants.  Equality with the
+unmodified release_server.GenerationSession and the reference-executed golden: tests/test_reference_callers_cpu.py."""
 import pytest
 import torch
 
@@ -12,7 +12,7 @@ from tests import cpu_ops_emulation as emu
 @pytest.fixture(autouse=True)
 def cpu_ops(monkeypatch):
     import realtime_video_b200.dit as dit
-    import realtime_video_b200.dropin.utils.wan_wrapper as ww
+    import realtime_video_b200.wan_wrapper as ww
     import realtime_video_b200.vae as vae
     for mod in (dit, ww, vae):
         monkeypatch.setattr(mod, "ops", emu)
@@ -20,10 +20,11 @@ def cpu_ops(monkeypatch):
 
 def make(keep_first_frame, decode=True, seed=7, blocks=4):
     from realtime_video_b200 import factory
-    from realtime_video_b200.session import GenerateParams, GenerationSession
+    import harness
+    from harness import GenerateParams, GenerationSession
     tr = factory.synthetic_transformer(size="tiny", device="cpu", dtype=torch.bfloat16, seed=0, dim=256, ffn_dim=512,
                                        num_heads=2, num_layers=2, text_dim=128)
-    models = factory.build_models(tr, vae_decoder=factory.synthetic_vae_decoder(device="cpu"), device="cpu",
+    models = harness.build_models(tr, vae_decoder=factory.synthetic_vae_decoder(device="cpu"), device="cpu",
                                   vae_encoder=factory.synthetic_vae_encoder(device="cpu"))
     calls = {"enc": 0}
     enc = models.vae_encoder

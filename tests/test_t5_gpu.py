@@ -1,11 +1,7 @@
 """GPU parity of the UMT5 encoder schedule (realtime_video_b200/t5.py through the C ABI, bf16 like the server runs it)
 against the reference T5Encoder goldens.  Tolerance: the reference's own bf16-vs-fp32 gap on this model is
 rel-L2 7e-3 (tests/golden/make_t5_goldens.py); we require <= 2e-2 against both goldens.
-
-The schedule only uses kernels that are validated elsewhere (kr_gemm, kr_rmsnorm, kr_softmax_rows), but this test
-itself was written after the round's GPU budget was spent and has not run on a B200 yet, hence non-strict xfail:
-a failure is reported as xfailed instead of stopping `pytest -x`, a pass shows up as xpassed.  The file name sorts last so that
-nothing runs after it in the same process."""
+"""
 import pytest
 import torch
 
@@ -14,7 +10,6 @@ from tests.golden_io import load_npz, rel_l2, weights
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.xfail(strict=False, reason="first B200 run pending (host schedule verified on CPU against the reference)")
 @pytest.mark.parametrize("tag", ["a", "b"])
 def test_t5_encoder_vs_reference_golden(tag):
     from realtime_video_b200.t5 import T5Encoder

@@ -53,7 +53,7 @@ def test_umt5_xxl_dimensions_and_keys():
 def test_drop_in_text_encoder_zeroes_padding_and_matches_oracle():
     """WanTextEncoder (utils/wan_wrapper.py:20-56) with an injected tokenizer: prompt_embeds [B, L, dim], rows past
     each prompt's length are zero, the valid rows equal the encoder output."""
-    import realtime_video_b200.dropin.utils.wan_wrapper as ww
+    import realtime_video_b200.wan_wrapper as ww
     from oracle.t5_oracle import T5EncoderOracle
     g = load_npz("t5_small.npz")
 
@@ -77,5 +77,5 @@ def test_drop_in_text_encoder_zeroes_padding_and_matches_oracle():
 
 
 def test_prompt_cleaning_matches_reference_rule():
-    from realtime_video_b200.dropin.utils.wan_wrapper import _PromptTokenizer
+    from realtime_video_b200.wan_wrapper import _PromptTokenizer
     assert _PromptTokenizer.clean("  a &amp;amp; b \n\t c  ") == "a & b c"

@@ -114,9 +114,9 @@ def test_streaming_encoder_chunks(g):
 def test_classic_wrapper_encode_to_latent(g):
     """WanVAEWrapper.encode_to_latent (utils/wan_wrapper.py:80-96): per sample a fresh 1 + 4 + 4 stream; the
     module tree accepts the reference's full WanVAE_ state dict (encoder.*, conv1.*, conv2.*, decoder.*)."""
-    import realtime_video_b200.dropin.utils.wan_wrapper as ww
+    import realtime_video_b200.wan_wrapper as ww
     gs = load_npz("vae_encoder_stream.npz")
-    w = ww.WanVAEWrapper()
+    w = ww.WanVAEWrapper(load_pretrained=False)
     sd = dict(synthetic_vae_params(seed=0, encoder=True))
     sd.update(synthetic_vae_params(seed=0))
     missing = w.model.load_state_dict(sd, strict=False)

@@ -6,7 +6,8 @@ import torch
 
 sys.path.insert(0, ".")
 from realtime_video_b200 import factory, ops  # noqa: E402
-from realtime_video_b200.session import GenerateParams, GenerationSession  # noqa: E402
+import harness  # noqa: E402
+from harness import GenerateParams, GenerationSession  # noqa: E402
 
 
 def parity():
@@ -27,7 +28,7 @@ def speed(layers):
     w = factory.synthetic_transformer("14B", num_layers=layers)
     torch.cuda.synchronize()
     print(f"built {layers}-layer 14B-dims model in {time.time() - t0:.1f}s, mem {torch.cuda.memory_allocated() / 1e9:.1f} GB", flush=True)
-    models = factory.build_models(w)
+    models = harness.build_models(w)
     pe = factory.synthetic_prompt_embeds()
     sess = GenerationSession(GenerateParams(num_blocks=4), models, prompt_embeds=pe, decode=False)
     for b in range(4):

@@ -7,13 +7,14 @@ import torch
 
 sys.path.insert(0, ".")
 from realtime_video_b200 import factory, ops  # noqa: E402
-from realtime_video_b200.session import GenerateParams, GenerationSession  # noqa: E402
+import harness  # noqa: E402
+from harness import GenerateParams, GenerationSession  # noqa: E402
 
 blocks = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 w = factory.synthetic_transformer("14B")
 vae = factory.synthetic_vae_decoder()
 enc = factory.synthetic_vae_encoder()
-models = factory.build_models(w, vae_decoder=vae, vae_encoder=enc)
+models = harness.build_models(w, vae_decoder=vae, vae_encoder=enc)
 pe = factory.synthetic_prompt_embeds()
 sess = GenerationSession(GenerateParams(width=1280, height=720, kv_cache_num_frames=5, num_blocks=blocks),
                          models, prompt_embeds=pe)
