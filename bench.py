@@ -14,9 +14,13 @@ value : frames/s with inputs resident in HBM, timed with CUDA events, max over r
 e2e   : same loop through the same public API (realtime_video_b200/dropin wrappers) with the
         block's noise copied from pinned host memory every step and the decoded fp32 frames
         copied back to pinned host memory inside the timed region.
-N > 1 : the path is one strictly sequential stream (B=1, step k+1 needs step k):
-        it does not shard, so N ranks run N independent replicas ("replicas only")
-        with no data-path collective; value = total frames of all ranks / max time.
+N > 1 : ONE video stream on all N GPUs (strong scaling; realtime_video_b200/parallel.py: token rows sharded for
+        everything token-wise, heads sharded for self-attention, the rows<->heads exchange written straight into the
+        peers' buffers over NVLink by the kernels).  value = frames of that one stream / max-over-ranks time.
+        The throughput-oriented alternative (N independent replicas, no data-path collective) is measured in
+        the same run and reported as the secondary key "replicas".  --parallel replicas makes it the headline.
+--workload vae_decode : VAE-decode-only throughput (BASELINE configs[4]): a stream of 3-latent-frame blocks through
+        the decoder with a warm feature cache; frames/s, conv TF/s and algorithmic HBM GB/s vs the measured peak.
 --impl reference : the reference algorithm on the host CPU cores (oracle port, torch fp32, all
         threads) on a bounded sample of the same workload, scaled to frames/s.
 """
@@ -186,7 +190,7 @@ class CpuReference:
                           f"block; VAE decode not included (would lower it further)"}
 
 
-def cpu_reference_sample(budget_s: float = 12.0, max_layers: int = 4) -> dict:
+def cpu_reference_sample(budget_s: float = 25.0, max_layers: int = 8) -> dict:
     ref = CpuReference()
     t_all = time.time()
     for i in range(max_layers):
@@ -247,6 +251,144 @@ def emit(line: dict):
         os.write(_JSON_FD, data)
 
 
+def _flat_roofline(prof: dict, ms_step: float, peaks: dict, traffic_db: dict) -> dict:
+    """roofline object for the dominant kernel family (the tcgen05 GEMMs) + flat per-kernel scalars.
+    ``prof`` comes from ONE separately profiled step (CUDA events around every launch of a family), never from the
+    timed region; ``share`` = family time / that step's time."""
+    def fam(name):
+        g = prof.get(name)
+        if not g or g["ms"] <= 0:
+            return None, None, 0
+        return g["flops"] / (g["ms"] * 1e-3) / 1e12, g["ms"] / ms_step, g["n"]
+    gem, gem_share, gem_n = fam("gemm")
+    out = {"bound": "tensor",
+           "kernel": "kr_gemm (tcgen05: gemm2_tn_kernel CTA-pair + gemm_tn_kernel single-CTA, all DiT linears)",
+           "achieved": gem, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": (gem / peaks["tensor"]) if gem else None,
+           "peak_source": peaks["source"], "launches_timed": gem_n, "share_of_step": gem_share,
+           "how": "algorithmic FLOPs of the launches / their CUDA-event time, from one extra profiled step after the "
+                  "timed region (the timed region itself carries no per-launch events)"}
+    by_kernel = {}
+    for label, key in (("gemm2", "gemm/gemm2_tn_kernel"), ("gemm1", "gemm/gemm_tn_kernel"),
+                       ("gemm_streamk", "gemm/gemm_sk_kernel"), ("attn", "attention"), ("vae_conv", "vae_conv")):
+        a, share, n = fam(key)
+        out[label + "_tflops"] = a
+        out[label + "_frac"] = (a / peaks["tensor"]) if a else None
+        out[label + "_share"] = share
+        if a is not None:
+            by_kernel[label] = {"achieved": a, "frac": a / peaks["tensor"], "launches_timed": n, "share_of_step": share}
+    dominant = max(("gemm2_tn_kernel", "gemm_tn_kernel"),
+                   key=lambda k: (prof.get("gemm/" + k) or {"ms": 0})["ms"])
+    out["traffic"] = traffic_db.get(dominant, {}).get("dram_bytes_per_launch")
+    out["traffic_kernel"] = dominant
+    out["by_kernel"] = by_kernel
+    return out
+
+
+def _traffic_db() -> dict:
+    for name in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+        tp = ROOT / "profiles" / name
+        if tp.exists():
+            try:
+                return json.loads(tp.read_text())
+            except Exception:  # noqa: BLE001
+                pass
+    return {}
+
+
+def run_vae_workload(args, dev, rank, world, barrier, max_over_ranks):
+    """BASELINE configs[4]: VAE-decode-only throughput at 832x480.  One step = one steady block (3 latent frames ->
+    12 pixel frames) of a running stream (warm feature cache); N > 1 = N independent streams (the decoder is one
+    causal stream; nothing to exchange)."""
+    from realtime_video_b200 import factory, ops
+    K, W = args.steps, max(3, args.warmup)
+    vae = factory.synthetic_vae_decoder(device=dev)
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    zs = [torch.randn(1, 3, 16, 60, 104, device=dev, dtype=torch.float16, generator=g) for _ in range(W + K + 1)]
+    host_z = [z.cpu().pin_memory() for z in zs]
+    host_px = torch.empty(1, 12, 3, 480, 832, dtype=torch.float32).pin_memory()
+    cache = [None] * 55
+    with torch.inference_mode():
+        for i in range(W):
+            px, cache = vae(zs[i], *cache)
+        barrier()
+        clocks = Clocks(dev.index)
+        if rank == 0:
+            clocks.start()
+        n0 = ops.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(W, W + K):
+            px, cache = vae(zs[i], *cache)
+        e1.record()
+        barrier()
+        launches = ops.launch_count - n0
+        clk = clocks.stop() if rank == 0 else None
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        # one profiled step (per-launch events) for the conv family's TF/s
+        ops.profile_begin()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        px, cache = vae(zs[W + K], *cache)
+        p1.record()
+        torch.cuda.synchronize()
+        prof = ops.profile_end()
+        ms_prof = p0.elapsed_time(p1)
+        # end to end: latents from pinned host memory, fp32 frames back to pinned host memory
+        cache2 = [None] * 55
+        zdev = torch.empty_like(zs[0])
+        for i in range(W):
+            px, cache2 = vae(zs[i], *cache2)
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(W, W + K):
+            zdev.copy_(host_z[i], non_blocking=True)
+            px, cache2 = vae(zdev, *cache2)
+            host_px.copy_(px, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        t1.record()
+        barrier()
+        ms_e2e = max_over_ranks(t0.elapsed_time(t1))
+    assert px.shape == (1, 12, 3, 480, 832)
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    vcv = prof.get("vae_conv", {"flops": 0.0, "ms": 0.0, "n": 0})
+    conv_tf = vcv["flops"] / (vcv["ms"] * 1e-3) / 1e12 if vcv["ms"] > 0 else None
+    # SURVEY.md §8d: >= 24.1 GB of conv input+output (fp16) per steady block if nothing is fused; irreducible
+    # (fully fused) = feature-cache read+write 3.8 GB + pixels 57.5 MB + weights 146.6 MB = 4.0 GB
+    ALG_UNFUSED, ALG_FUSED = 24.1e9, 4.0e9
+    gbs = ALG_UNFUSED / (ms / K * 1e-3) / 1e9
+    vt = {}
+    tp = ROOT / "profiles" / "r02_vae_traffic.json"
+    if tp.exists():
+        try:
+            vt = json.loads(tp.read_text())
+        except Exception:  # noqa: BLE001
+            vt = {}
+    line = {"metric": "vae_decode_frames_per_second_832x480", "value": world * K * 12 / (ms / 1e3), "unit": "frames/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "vae_decode_832x480_block12f", "latent": "[1,3,16,60,104] fp16 per step, warm feature cache",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} independent decoder streams",
+                       "l2": "each layer's activations (0.9 GB at 480x832) exceed the 126 MB L2; no flush needed"},
+            "e2e": {"value": world * K * 12 / (ms_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_e2e / K,
+                    "h2d_bytes_per_step": host_z[0].numel() * 2, "d2h_bytes_per_step": host_px.numel() * 4},
+            "gpu_launches": launches, "clocks": clk,
+            "roofline": {"bound": "tensor", "kernel": "conv_halo_kernel / conv_igemm_kernel (implicit-GEMM causal conv3d)",
+                         "achieved": conv_tf, "peak": peaks["tensor"], "unit": "TFLOP/s",
+                         "frac": conv_tf / peaks["tensor"] if conv_tf else None, "peak_source": peaks["source"],
+                         "share_of_step": vcv["ms"] / ms_prof if ms_prof > 0 else None, "launches_timed": vcv["n"],
+                         "traffic": vt.get("dram_bytes_per_block"),
+                         "hbm": {"algorithmic_gb_per_block_unfused": ALG_UNFUSED / 1e9,
+                                 "algorithmic_gb_per_block_fully_fused": ALG_FUSED / 1e9,
+                                 "achieved_gbs_vs_unfused_bytes": gbs, "peak_gbs": peaks["hbm"],
+                                 "frac_of_hbm_peak": gbs / peaks["hbm"],
+                                 "measured_dram_gb_per_block": (vt.get("dram_bytes_per_block") or 0) / 1e9 or None}},
+            "cpu_baseline": None}
+    emit(line)
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -254,12 +396,14 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--parallel", default="replicas", choices=["replicas", "sp"],
-                    help="N>1: independent replicas (default; the path does not shard) or ONE stream "
-                         "sequence-parallel over all GPUs (realtime_video_b200/parallel.py)")
+    ap.add_argument("--parallel", default="sp", choices=["replicas", "sp"],
+                    help="N>1 headline: ONE stream sequence-parallel over all GPUs (default, strong scaling; "
+                         "realtime_video_b200/parallel.py) or N independent replicas (weak scaling)")
+    ap.add_argument("--workload", default="block", choices=["block", "vae_decode"])
     ap.add_argument("--layers", type=int, default=LAYERS, help=argparse.SUPPRESS)      # debugging only
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-egress", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-secondary", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -280,16 +424,6 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(tempfile.gettempdir(), "nccl_bench.%h.%p.log"))
         dist.init_process_group("nccl", device_id=dev)
 
-    from realtime_video_b200 import factory, ops
-    import harness
-    from harness import GenerateParams, GenerationSession
-    K, W = args.steps, args.warmup
-    transformer = factory.synthetic_transformer("14B", device=dev, num_layers=args.layers, seed=0)
-    vae = factory.synthetic_vae_decoder(device=dev)
-    vae_enc = factory.synthetic_vae_encoder(device=dev)
-    models = harness.build_models(transformer, vae_decoder=vae, device=dev, vae_encoder=vae_enc)
-    pe = factory.synthetic_prompt_embeds(device=dev)
-
     def barrier():
         if world > 1:
             import torch.distributed as dist
@@ -304,94 +438,129 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---------------- device-resident run (value) ----------------
+    if args.workload == "vae_decode":
+        run_vae_workload(args, dev, rank, world, barrier, max_over_ranks)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    import harness
+    from harness import GenerateParams, GenerationSession
+    from realtime_video_b200 import factory, ops
+    K, W = args.steps, args.warmup
+    transformer = factory.synthetic_transformer("14B", device=dev, num_layers=args.layers, seed=0)
+    vae = factory.synthetic_vae_decoder(device=dev)
+    vae_enc = factory.synthetic_vae_encoder(device=dev)
+    models = harness.build_models(transformer, vae_decoder=vae, device=dev, vae_encoder=vae_enc)
+    pe = factory.synthetic_prompt_embeds(device=dev)
     sp_mode = world > 1 and args.parallel == "sp"
-    streams = 1 if sp_mode else world           # independent video streams in flight
-    if sp_mode:
-        from realtime_video_b200.parallel import SequenceParallel
-        transformer.model.sp = SequenceParallel()
-    decode = (not sp_mode) or rank == 0         # one stream -> one VAE decode (rank 0)
-    params = GenerateParams(num_blocks=W + K, seed=42 + (0 if sp_mode else rank))
-    sess = GenerationSession(params, models, prompt_embeds=pe, device=dev, decode=decode)
-    with torch.inference_mode():
-        for _ in range(W):
-            sess.generate_block()
-        barrier()
-        clocks = Clocks(local)
-        if rank == 0:
-            clocks.start()
-        ops.profile_begin()
-        n0 = ops.launch_count
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(K):
-            px = sess.generate_block()
-        e1.record()
-        barrier()
-        launches = ops.launch_count - n0
-        prof = ops.profile_end()
-        clk = clocks.stop() if rank == 0 else None
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    if decode:
-        assert px.shape == (1, 12, 3, 480, 832) and px.dtype == torch.float32
-    value = streams * K * FRAMES_PER_STEP / (ms / 1e3)
 
-    # ---------------- end-to-end run (host buffers) ----------------
-    nf = 3
-    sess2 = GenerationSession(GenerateParams(num_blocks=W + K, seed=1042 + (0 if sp_mode else rank)), models,
-                              prompt_embeds=pe, device=dev, decode=decode)
-    host_noise = sess2.noise.cpu().pin_memory()
-    host_px = torch.empty(1, 12, 3, 480, 832, dtype=torch.float32).pin_memory()
-    with torch.inference_mode():
-        for _ in range(W):
-            sess2.generate_block()
-        barrier()
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record()
-        for _ in range(K):
-            s = sess2.current_start_frame
-            sess2.noise[:, s:s + nf].copy_(host_noise[:, s:s + nf], non_blocking=True)      # H2D
-            px = sess2.generate_block()
-            if decode:
-                host_px.copy_(px, non_blocking=True)                                        # D2H
-            torch.cuda.current_stream().synchronize()                                       # frames usable on host
-        t1.record()
-        barrier()
-    ms_e2e = max_over_ranks(t0.elapsed_time(t1))
-    e2e = streams * K * FRAMES_PER_STEP / (ms_e2e / 1e3)
-    h2d = host_noise[:, :nf].numel() * host_noise.element_size()
-    d2h = host_px.numel() * host_px.element_size()
-
-    # ---------------- same end-to-end loop with the byte egress kernel ----------------
-    # kr_frames_to_rgb8 does the reference's host-side normalise + to_pil_image conversion on the device, so
-    # uint8 [12, H, W, 3] (14.4 MB) instead of fp32 (57.5 MB) crosses PCIe.  Reported next to `e2e`, which keeps
-    # the reference's own fp32 download.
-    egress = None
-    if decode and not sp_mode and not args.no_egress:
-        sess3 = GenerationSession(GenerateParams(num_blocks=W + K, seed=2042 + rank), models,
-                                  prompt_embeds=pe, device=dev, decode=True)
-        host_noise3 = sess3.noise.cpu().pin_memory()
-        host_rgb = torch.empty(1, 12, 480, 832, 3, dtype=torch.uint8).pin_memory()
-        dev_rgb = torch.empty(1, 12, 480, 832, 3, dtype=torch.uint8, device=dev)
+    def measure(sp: bool, steps: int, seed: int, profile_step: bool):
+        """W warm-up blocks, then ``steps`` timed blocks (CUDA events, barrier + synchronize on both sides, max over
+        ranks); optionally ONE more block with per-launch events for the kernel split."""
+        if sp:
+            from realtime_video_b200.parallel import SequenceParallel
+            if transformer.model.sp is None:
+                transformer.model.sp = SequenceParallel()
+        else:
+            transformer.model.sp = None
+        decode = (not sp) or rank == 0              # one stream -> one VAE decode (rank 0)
+        sess = GenerationSession(GenerateParams(num_blocks=W + steps + 1, seed=seed + (0 if sp else rank)), models,
+                                 prompt_embeds=pe, device=dev, decode=decode)
+        out = {"decode": decode}
         with torch.inference_mode():
             for _ in range(W):
-                sess3.generate_block()
+                sess.generate_block()
             barrier()
-            u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            u0.record()
-            for _ in range(K):
-                s3 = sess3.current_start_frame
-                sess3.noise[:, s3:s3 + nf].copy_(host_noise3[:, s3:s3 + nf], non_blocking=True)
-                px3 = sess3.generate_block()
-                ops.frames_to_rgb8(px3, out=dev_rgb)
-                host_rgb.copy_(dev_rgb, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-            u1.record()
+            clocks = Clocks(local)
+            if rank == 0:
+                clocks.start()
+            n0 = ops.launch_count
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                px = sess.generate_block()
+            e1.record()
             barrier()
-        ms_rgb = max_over_ranks(u0.elapsed_time(u1))
-        egress = {"value": streams * K * FRAMES_PER_STEP / (ms_rgb / 1e3), "unit": "frames/s",
-                  "d2h_bytes_per_step": host_rgb.numel(), "ms_per_step": ms_rgb / K,
+            out["launches"] = ops.launch_count - n0
+            out["clocks"] = clocks.stop() if rank == 0 else None
+            out["ms"] = max_over_ranks(e0.elapsed_time(e1))
+            if decode:
+                assert px.shape == (1, 12, 3, 480, 832) and px.dtype == torch.float32
+            if profile_step:
+                barrier()
+                ops.profile_begin()
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
+                sess.generate_block()
+                p1.record()
+                barrier()
+                out["prof"], out["ms_prof"] = ops.profile_end(), p0.elapsed_time(p1)
+        return out
+
+    def measure_e2e(sp: bool, steps: int, seed: int, rgb8: bool = False):
+        """Same loop through the same public API with HOST buffers: the block's noise from pinned host memory every
+        step and the decoded frames back to pinned host memory inside the timed region."""
+        decode = (not sp) or rank == 0
+        sess = GenerationSession(GenerateParams(num_blocks=W + steps, seed=seed + (0 if sp else rank)), models,
+                                 prompt_embeds=pe, device=dev, decode=decode)
+        nf = 3
+        host_noise = sess.noise.cpu().pin_memory()
+        if rgb8:
+            host_out = torch.empty(1, 12, 480, 832, 3, dtype=torch.uint8).pin_memory()
+            dev_rgb = torch.empty(1, 12, 480, 832, 3, dtype=torch.uint8, device=dev)
+        else:
+            host_out = torch.empty(1, 12, 3, 480, 832, dtype=torch.float32).pin_memory()
+        with torch.inference_mode():
+            for _ in range(W):
+                sess.generate_block()
+            barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(steps):
+                s0 = sess.current_start_frame
+                sess.noise[:, s0:s0 + nf].copy_(host_noise[:, s0:s0 + nf], non_blocking=True)      # H2D
+                px = sess.generate_block()
+                if decode:
+                    if rgb8:
+                        ops.frames_to_rgb8(px, out=dev_rgb)
+                        host_out.copy_(dev_rgb, non_blocking=True)
+                    else:
+                        host_out.copy_(px, non_blocking=True)                                   # D2H
+                torch.cuda.current_stream().synchronize()                                       # frames usable on host
+            t1.record()
+            barrier()
+        return {"ms": max_over_ranks(t0.elapsed_time(t1)),
+                "h2d": host_noise[:, :nf].numel() * host_noise.element_size(),
+                "d2h": host_out.numel() * host_out.element_size()}
+
+    streams = 1 if sp_mode else world           # independent video streams in flight
+    main_run = measure(sp_mode, K, 42, profile_step=True)
+    ms = main_run["ms"]
+    value = streams * K * FRAMES_PER_STEP / (ms / 1e3)
+    e2e_run = measure_e2e(sp_mode, K, 1042)
+    e2e = streams * K * FRAMES_PER_STEP / (e2e_run["ms"] / 1e3)
+
+    # same end-to-end loop with the byte egress kernel (SURVEY.md 8f.2): kr_frames_to_rgb8 does the reference's
+    # host-side normalise + to_pil_image conversion on the device, so uint8 [12,H,W,3] (14.4 MB) instead of fp32
+    # (57.5 MB) crosses PCIe.  Reported next to `e2e`, which keeps the reference's own fp32 download.
+    egress = None
+    if not sp_mode and not args.no_egress:
+        r = measure_e2e(False, K, 2042, rgb8=True)
+        egress = {"value": streams * K * FRAMES_PER_STEP / (r["ms"] / 1e3), "unit": "frames/s",
+                  "d2h_bytes_per_step": r["d2h"], "ms_per_step": r["ms"] / K,
                   "what": "e2e loop with kr_frames_to_rgb8 on the device and a uint8 [12,480,832,3] download"}
+
+    # N > 1: the other way to use the box (N independent replicas, no data-path collective), same run
+    secondary = None
+    if world > 1 and not args.no_secondary:
+        other = measure(not sp_mode, max(2, K // 2), 3042, profile_step=False)
+        n_streams = world if sp_mode else 1
+        secondary = {"mode": "replicas" if sp_mode else "sp", "scaling": "weak" if sp_mode else "strong",
+                     "value": n_streams * max(2, K // 2) * FRAMES_PER_STEP / (other["ms"] / 1e3), "unit": "frames/s",
+                     "ms_per_step": other["ms"] / max(2, K // 2), "steps": max(2, K // 2)}
 
     if world > 1:
         import torch.distributed as dist
@@ -400,43 +569,7 @@ def main():
     if rank != 0:
         return
     peaks = measured_peaks()
-    # roofline of the dominant kernel family (tcgen05 GEMMs): algorithmic FLOPs / CUDA-event time of its
-    # launches, plus the split between the two kernels behind kr_gemm (CTA-pair / single-CTA)
-    gem = prof.get("gemm", {"flops": 0.0, "ms": 0.0, "n": 0})
-    att = prof.get("attention", {"flops": 0.0, "ms": 0.0, "n": 0})
-    vcv = prof.get("vae_conv", {"flops": 0.0, "ms": 0.0, "n": 0})
-    achieved = gem["flops"] / (gem["ms"] * 1e-3) / 1e12 if gem["ms"] > 0 else None
-    traffic_db = {}
-    tp = ROOT / "profiles" / "r01_gemm_traffic.json"
-    if tp.exists():
-        try:
-            traffic_db = json.loads(tp.read_text())
-        except Exception:  # noqa: BLE001
-            traffic_db = {}
-    by_kernel = {}
-    for name in ("gemm2_tn_kernel", "gemm_tn_kernel"):
-        g = prof.get("gemm/" + name)
-        if g and g["ms"] > 0:
-            a = g["flops"] / (g["ms"] * 1e-3) / 1e12
-            by_kernel[name] = {"achieved": a, "frac": a / peaks["tensor"], "launches_timed": g["n"],
-                               "share_of_step": g["ms"] / ms if ms > 0 else None,
-                               "traffic": traffic_db.get(name, {}).get("dram_bytes_per_launch")}
-    dominant = max(by_kernel, key=lambda k: by_kernel[k]["share_of_step"] or 0.0) if by_kernel else None
-    roofline = {"bound": "tensor", "kernel": "kr_gemm (tcgen05: gemm2_tn_kernel CTA-pair + gemm_tn_kernel single-CTA, all DiT linears)",
-                "achieved": achieved,
-                "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": (achieved / peaks["tensor"]) if achieved else None,
-                "traffic": traffic_db.get(dominant, {}).get("dram_bytes_per_launch") if dominant else None,
-                "traffic_kernel": dominant,
-                "peak_source": peaks["source"], "launches_timed": gem["n"],
-                "share_of_step": (gem["ms"] / (ms / 1.0)) if ms > 0 else None,
-                "by_kernel": by_kernel,
-                "attention": {"achieved": att["flops"] / (att["ms"] * 1e-3) / 1e12 if att["ms"] > 0 else None,
-                              "unit": "TFLOP/s", "launches_timed": att["n"],
-                              "share_of_step": att["ms"] / ms if ms > 0 else None},
-                # VAE (decoder + first-frame encoder) implicit-GEMM convs: 2*taps*Cin*Cout*pixels per launch
-                "vae_conv": {"achieved": vcv["flops"] / (vcv["ms"] * 1e-3) / 1e12 if vcv["ms"] > 0 else None,
-                             "unit": "TFLOP/s", "launches_timed": vcv["n"],
-                             "share_of_step": vcv["ms"] / ms if ms > 0 else None}}
+    roofline = _flat_roofline(main_run["prof"], main_run["ms_prof"], peaks, _traffic_db())
     block_tflop = (4 * LAYERS * layer_flops(LQ, LKV) + LAYERS * layer_flops(LQ, LQ)) / 1e12 * (args.layers / LAYERS)
     cpu = None
     if not args.no_cpu_baseline:
@@ -444,30 +577,37 @@ def main():
             cpu = cpu_reference_sample()
         except Exception as ex:  # noqa: BLE001
             cpu = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+    if sp_mode:
+        par = (f"ONE stream on {world} GPUs: token rows sharded for all token-wise kernels, heads sharded for "
+               f"self-attention; the rows<->heads exchange is done by the kernels over NVLink peer memory "
+               f"(realtime_video_b200/parallel.py); VAE decode on rank 0")
+    else:
+        par = "1 GPU" if world == 1 else f"{world} independent replicas (no data-path collective)"
     line = {
         "metric": "frames_per_second_832x480_4step_t2v", "value": value, "unit": "frames/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
-        "scaling": "strong" if sp_mode else "weak", "vs_baseline": (value / 11.0) if world == 1 else None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "strong" if sp_mode else "weak", "vs_baseline": (value / 11.0) if world == 1 else None,
+        "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "dims": "Wan2.1-T2V-14B (40 layers, d 5120, ffn 13824, 40 heads)"
                    if args.layers == LAYERS else f"DEBUG {args.layers} layers",
                    "resolution": "832x480", "denoise_steps": 4, "kv_cache_num_frames": 3, "frames_per_step": 12,
                    "passes_per_step": "1-frame VAE encode + 1 KV recompute + 4 denoise DiT passes + VAE decode (fp16)",
                    "first_frame": "re-encoded from the oldest cached pixel frame once the window slides "
                                   "(reference default keep_first_frame=False, release_server.py:571-576)",
-                   "parallelism": "1 GPU" if world == 1 else (
-                       f"ONE stream, Ulysses sequence parallel over {world} GPUs (rows<->heads all-to-all, NCCL); "
-                       f"VAE decode on rank 0" if sp_mode else f"{world} independent replicas (path does not shard)"),
+                   "parallelism": par,
                    "l2": "weights (28 GB/pass) and KV cache exceed the 126 MB L2 every step; no flush needed",
                    "dit_tflop_per_step": block_tflop},
         "egress_rgb8": egress,
-        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / K},
-        "gpu_launches": launches,
-        "clocks": clk,
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": e2e_run["h2d"],
+                "d2h_bytes_per_step": e2e_run["d2h"], "ms_per_step": e2e_run["ms"] / K},
+        "gpu_launches": main_run["launches"],
+        "clocks": main_run["clocks"],
         "roofline": roofline,
         "cpu_baseline": cpu,
         "baseline_note": "vs_baseline = value / 11 fps (reference README.md:31: 11 fps on 1x B200, 4 steps); null for N>1 (nothing published)",
     }
+    if secondary is not None:
+        line[secondary["mode"]] = secondary
     emit(line)
 
 

@@ -50,6 +50,13 @@ class PipelineState(torch.nn.Module):
                 c["v"].zero_()
                 c["global_end_index"] = c["local_end_index"] = 0
             return
+        sp = getattr(self.generator.model, "sp", None)
+        if sp is not None and sp.p2p:
+            # multi-GPU single-stream mode: the caches live in the rank's symmetric allocation so that the peers'
+            # kernels can store K / V rows straight into them (realtime_video_b200/parallel.py)
+            kv = sp.alloc_kv_cache(self.num_transformer_blocks, shape, dtype, device)
+            self.kv_cache1 = [dict(k=k, v=v, global_end_index=0, local_end_index=0) for k, v in kv]
+            return
         self.kv_cache1 = [dict(k=torch.zeros(shape, dtype=dtype, device=device),
                                v=torch.zeros(shape, dtype=dtype, device=device),
                                global_end_index=0, local_end_index=0) for _ in range(self.num_transformer_blocks)]

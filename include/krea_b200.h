@@ -60,10 +60,23 @@ int kr_gemm(int dtype, int epilogue, const void* a, int lda, const void* w, int 
             int ldr, const void* gate, int gate_stride, int rows_per_gate, float alpha,
             void* out2, int ldc2, int n_split, int row_offset, void* stream);
 
+/* kr_gemm with a caller-owned workspace: kr_gemm_workspace_bytes() bytes of device memory, zero-filled ONCE by the
+ * caller and then private to the stream the calls are issued on.  With it, shapes whose output-tile count does not
+ * fill the SMs (e.g. the M = 4680/N-row shards of the multi-GPU mode) run on the stream-K kernel: equal shares of
+ * (tile, k-block) MMA iterations per SM, fp32 partial tiles exchanged through the workspace, the last contributor
+ * of a tile sums them in CTA order and runs the fused epilogue.  workspace == NULL behaves exactly like kr_gemm. */
+int kr_gemm_ws(int dtype, int epilogue, const void* a, int lda, const void* w, int ldw,
+               const void* bias, void* out, int ldc, int M, int N, int K, const void* residual,
+               int ldr, const void* gate, int gate_stride, int rows_per_gate, float alpha,
+               void* out2, int ldc2, int n_split, int row_offset, void* workspace, size_t workspace_bytes,
+               void* stream);
+size_t kr_gemm_workspace_bytes(void);
+
 /* Which kernel kr_gemm launches for this epilogue and shape: 1 = the single-CTA kernel, 2 = the CTA-pair
- * kernel (tcgen05.mma.cta_group::2, 256x256 tiles).  Host-only query (no launch), used by bench.py to
- * attribute launch time per kernel. */
+ * kernel (tcgen05.mma.cta_group::2, 256x256 tiles), 3 = the stream-K kernel (only with a workspace).  Host-only
+ * queries (no launch), used by bench.py to attribute launch time per kernel. */
 int kr_gemm_kernel_id(int epilogue, int M, int N, int K);
+int kr_gemm_kernel_id_ws(int epilogue, int M, int N, int K, int have_workspace);
 
 /* softmax(scale * q k^T) v, head_dim 128, [L, heads, 128] layout, bf16/fp16, fp32 softmax.
  * mask_mode 0: none (cached self-attention causal_model.py:386-390, cross-attention
@@ -90,6 +103,24 @@ int kr_qkv_norm_rope(const void* q, int ldq, const void* k, int ldk, const void*
                      const void* wq, const void* wk, void* q_out, int ldqo, void* k_out, int ldko,
                      void* v_out, int ldvo, const void* rope, int rows, int D, int head_dim,
                      int grid_h, int grid_w, int start_frame, int row_offset, float eps, void* stream);
+
+/* Multi-GPU single-stream mode (SURVEY.md 8e option 3: token rows sharded, heads sharded for self-attention).
+ * kr_qkv_norm_rope_p2p = kr_qkv_norm_rope whose stores ARE the rows->heads exchange: the columns of rank d's heads
+ * ([d*peer_cols, (d+1)*peer_cols)) of every local row are written straight into rank d's q buffer / K-cache slot /
+ * V-cache slot over NVLink peer memory (16-byte remote stores); *_peer[d] addresses this rank's first row inside
+ * rank d's buffer (caller-owned symmetric allocations whose peer addresses the caller exchanged, e.g. through
+ * torch.distributed._symmetric_memory); world <= 8.  kr_comm_scatter_rows is the way back: rows
+ * [r*rows_per_peer, (r+1)*rows_per_peer) of the attention output of MY heads go to rank r's row-sharded buffer at
+ * MY column block.  Both replace an NCCL all_to_all + pack/unpack copies; ordering across ranks is the caller's
+ * (a barrier between the exchange and its consumer).  The reference is single-GPU (release_server.py:111-119 only
+ * replicates models); these entry points have no reference counterpart. */
+int kr_qkv_norm_rope_p2p(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
+                         const void* wq, const void* wk, void* const* q_peer, int ldqo, void* const* k_peer,
+                         int ldko, void* const* v_peer, int ldvo, int world, int peer_cols, const void* rope,
+                         int rows, int D, int head_dim, int grid_h, int grid_w, int start_frame, int row_offset,
+                         float eps, void* stream);
+int kr_comm_scatter_rows(const void* src, int ld_src, void* const* dst_peer, int ld_dst, int rows, int cols,
+                         int rows_per_peer, int world, void* stream);
 
 /* WanRMSNorm rows (cross-attention q / k): model.py:69-85, :183-190 */
 int kr_rmsnorm(const void* x, int ldx, void* out, int ldo, const void* w, int rows, int D,

@@ -16,7 +16,7 @@ from pathlib import Path
 _PKG_DIR = Path(__file__).resolve().parent
 _CSRC = _PKG_DIR / "csrc"
 LIB_PATH = _PKG_DIR / "libkrea_b200.so"
-SOURCES = ["kr_host.cu", "kr_gemm.cu", "kr_gemm2.cu", "kr_attn.cu", "kr_dit_elem.cu", "kr_vae.cu", "kr_api.cu"]
+SOURCES = ["kr_host.cu", "kr_gemm.cu", "kr_gemm2.cu", "kr_gemm_sk.cu", "kr_attn.cu", "kr_dit_elem.cu", "kr_vae.cu", "kr_api.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -92,12 +92,18 @@ _sz = ctypes.c_size_t
 # name -> argtypes; every function returns int except where noted
 SIGNATURES = {
     "kr_gemm_kernel_id": [_i, _i, _i, _i],
+    "kr_gemm_kernel_id_ws": [_i, _i, _i, _i, _i],
+    "kr_gemm_ws": [_i, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _f, _vp, _i, _i,
+                   _i, _vp, _sz, _vp],
     "kr_gemm": [_i, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _f, _vp, _i, _i,
                 _i, _vp],
     "kr_attn_fwd": [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _f, _i, _i, _i, _i, _vp],
     "kr_ln_modulate": [_vp, _i, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "kr_qkv_norm_rope": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i,
                          _i, _i, _i, _i, _i, _i, _f, _vp],
+    "kr_qkv_norm_rope_p2p": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp,
+                             _i, _i, _i, _i, _i, _i, _i, _f, _vp],
+    "kr_comm_scatter_rows": [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "kr_rmsnorm": [_vp, _i, _vp, _i, _vp, _i, _i, _f, _vp],
     "kr_add_modulation": [_vp, _vp, _i, _vp, _i, _i, _i, _vp],
     "kr_activation": [_vp, _vp, _sz, _i, _vp],
@@ -130,6 +136,8 @@ def load() -> ctypes.CDLL:
         lib.kr_version.argtypes = []
         lib.kr_last_error.restype = ctypes.c_char_p
         lib.kr_last_error.argtypes = []
+        lib.kr_gemm_workspace_bytes.restype = _sz
+        lib.kr_gemm_workspace_bytes.argtypes = []
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name, None)
             if fn is None:

@@ -20,11 +20,24 @@ int kr_version(void) { return 100; }
 const char* kr_last_error(void) { return kr::last_error(); }
 
 int kr_gemm_kernel_id(int epilogue, int M, int N, int K) { return kr::gemm_plan(epilogue, M, N, K) + 1; }
+int kr_gemm_kernel_id_ws(int epilogue, int M, int N, int K, int have_workspace) {
+  return kr::gemm_plan(epilogue, M, N, K, have_workspace != 0) + 1;
+}
+size_t kr_gemm_workspace_bytes(void) { return kr::gemm_sk_workspace_bytes(); }
 
 int kr_gemm(int dtype, int epilogue, const void* a, int lda, const void* w, int ldw,
             const void* bias, void* out, int ldc, int M, int N, int K, const void* residual,
             int ldr, const void* gate, int gate_stride, int rows_per_gate, float alpha,
             void* out2, int ldc2, int n_split, int row_offset, void* stream) {
+  return kr_gemm_ws(dtype, epilogue, a, lda, w, ldw, bias, out, ldc, M, N, K, residual, ldr, gate, gate_stride,
+                    rows_per_gate, alpha, out2, ldc2, n_split, row_offset, nullptr, 0, stream);
+}
+
+int kr_gemm_ws(int dtype, int epilogue, const void* a, int lda, const void* w, int ldw,
+               const void* bias, void* out, int ldc, int M, int N, int K, const void* residual,
+               int ldr, const void* gate, int gate_stride, int rows_per_gate, float alpha,
+               void* out2, int ldc2, int n_split, int row_offset, void* workspace, size_t workspace_bytes,
+               void* stream) {
   KR_REQUIRE(a && w && out, "null a/w/out");
   KR_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (bf16) or 1 (fp16)");
   kr::GemmParams p;
@@ -32,7 +45,7 @@ int kr_gemm(int dtype, int epilogue, const void* a, int lda, const void* w, int 
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.ldr = ldr; p.gate_stride = gate_stride;
   p.rows_per_gate = rows_per_gate; p.alpha = alpha;
   p.out2 = out2; p.ldc2 = ldc2; p.n_split = n_split; p.row_offset = row_offset;
-  return kr::gemm_tn(dtype, epilogue, a, lda, w, ldw, p, static_cast<cudaStream_t>(stream));
+  return kr::gemm_tn(dtype, epilogue, a, lda, w, ldw, p, static_cast<cudaStream_t>(stream), workspace, workspace_bytes);
 }
 
 int kr_attn_fwd(int dtype, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
@@ -74,7 +87,44 @@ int kr_qkv_norm_rope(const void* q, int ldq, const void* k, int ldk, const void*
   p.D = D; p.head_dim = head_dim; p.grid_h = grid_h; p.grid_w = grid_w; p.start_frame = start_frame;
   p.row_offset = row_offset;
   p.eps = eps;
+  p.peer_cols = 0;
   return kr::qkv_post(p, rows, static_cast<cudaStream_t>(stream));
+}
+
+int kr_qkv_norm_rope_p2p(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
+                         const void* wq, const void* wk, void* const* q_peer, int ldqo, void* const* k_peer,
+                         int ldko, void* const* v_peer, int ldvo, int world, int peer_cols, const void* rope,
+                         int rows, int D, int head_dim, int grid_h, int grid_w, int start_frame, int row_offset,
+                         float eps, void* stream) {
+  KR_REQUIRE(q && k && v && wq && wk && q_peer && k_peer && v_peer, "null q/k/v/weights/peer tables");
+  KR_REQUIRE(world >= 1 && world <= 8, "world must be 1..8");
+  KR_REQUIRE(peer_cols > 0 && peer_cols % head_dim == 0 && peer_cols * world == D, "peer_cols * world must equal D");
+  kr::QkvPostParams p;
+  p.q = static_cast<const uint16_t*>(q); p.k = static_cast<const uint16_t*>(k);
+  p.v = static_cast<const uint16_t*>(v);
+  p.ldq = ldq; p.ldk = ldk; p.ldv = ldv;
+  p.wq = static_cast<const uint16_t*>(wq); p.wk = static_cast<const uint16_t*>(wk);
+  p.q_out = nullptr; p.k_out = nullptr; p.v_out = nullptr;
+  p.ldqo = ldqo; p.ldko = ldko; p.ldvo = ldvo;
+  p.rope = static_cast<const float2*>(rope);
+  p.D = D; p.head_dim = head_dim; p.grid_h = grid_h; p.grid_w = grid_w; p.start_frame = start_frame;
+  p.row_offset = row_offset;
+  p.eps = eps;
+  p.peer_cols = peer_cols;
+  for (int i = 0; i < 8; ++i) {
+    p.q_peer[i] = i < world ? static_cast<uint16_t*>(q_peer[i]) : nullptr;
+    p.k_peer[i] = i < world ? static_cast<uint16_t*>(k_peer[i]) : nullptr;
+    p.v_peer[i] = i < world ? static_cast<uint16_t*>(v_peer[i]) : nullptr;
+    if (i < world) KR_REQUIRE(p.q_peer[i] && p.k_peer[i] && p.v_peer[i], "null peer pointer");
+  }
+  return kr::qkv_post(p, rows, static_cast<cudaStream_t>(stream));
+}
+
+int kr_comm_scatter_rows(const void* src, int ld_src, void* const* dst_peer, int ld_dst, int rows, int cols,
+                         int rows_per_peer, int world, void* stream) {
+  KR_REQUIRE(src && dst_peer, "null src / peer table");
+  return kr::p2p_scatter_rows(src, ld_src, dst_peer, ld_dst, rows, cols, rows_per_peer, world,
+                              static_cast<cudaStream_t>(stream));
 }
 
 int kr_rmsnorm(const void* x, int ldx, void* out, int ldo, const void* w, int rows, int D,

@@ -215,8 +215,9 @@ __global__ void __launch_bounds__(kRowThreads, 6) qkv_post_kernel(const QkvPostP
   const int c = p.head_dim >> 1;
   const int c_h = c / 3, c_t = c - 2 * c_h;
 
-  uint16_t* qo = p.q_out + static_cast<size_t>(row) * p.ldqo;
-  uint16_t* ko = p.k_out + static_cast<size_t>(row) * p.ldko;
+  const bool peers = p.peer_cols > 0;
+  uint16_t* qo = peers ? nullptr : p.q_out + static_cast<size_t>(row) * p.ldqo;
+  uint16_t* ko = peers ? nullptr : p.k_out + static_cast<size_t>(row) * p.ldko;
 #pragma unroll
   for (int i = 0; i < kVec; ++i) {
     const int vi = threadIdx.x + i * kRowThreads;
@@ -254,16 +255,65 @@ __global__ void __launch_bounds__(kRowThreads, 6) qkv_post_kernel(const QkvPostP
           b[2 * j + 1] = b0 * cs.y + b1 * cs.x;
         }
       }
-      store8(qo + vi * 8, a);
-      store8(ko + vi * 8, b);
+      if (peers) {
+        // heads [d*peer_cols/head_dim, ...) belong to rank d: remote 16-byte stores over NVLink
+        const int d = (vi * 8) / p.peer_cols, col = (vi * 8) - d * p.peer_cols;
+        store8(p.q_peer[d] + static_cast<size_t>(row) * p.ldqo + col, a);
+        store8(p.k_peer[d] + static_cast<size_t>(row) * p.ldko + col, b);
+      } else {
+        store8(qo + vi * 8, a);
+        store8(ko + vi * 8, b);
+      }
     }
   }
   if (p.v != nullptr) {
     const uint16_t* vr = p.v + static_cast<size_t>(row) * p.ldv;
-    uint16_t* vo = p.v_out + static_cast<size_t>(row) * p.ldvo;
-    for (int vi = threadIdx.x; vi < nvec; vi += kRowThreads)
-      *reinterpret_cast<uint4*>(vo + vi * 8) = *reinterpret_cast<const uint4*>(vr + vi * 8);
+    if (peers) {
+      for (int vi = threadIdx.x; vi < nvec; vi += kRowThreads) {
+        const int d = (vi * 8) / p.peer_cols, col = (vi * 8) - d * p.peer_cols;
+        *reinterpret_cast<uint4*>(p.v_peer[d] + static_cast<size_t>(row) * p.ldvo + col) =
+            *reinterpret_cast<const uint4*>(vr + vi * 8);
+      }
+    } else {
+      uint16_t* vo = p.v_out + static_cast<size_t>(row) * p.ldvo;
+      for (int vi = threadIdx.x; vi < nvec; vi += kRowThreads)
+        *reinterpret_cast<uint4*>(vo + vi * 8) = *reinterpret_cast<const uint4*>(vr + vi * 8);
+    }
   }
+}
+
+// ---------------------------------------------------------------------------
+// rows of src -> the peer that owns them (attention output back from head-sharded to row-sharded)
+// ---------------------------------------------------------------------------
+struct ScatterPeers { uint16_t* dst[8]; };
+__global__ void __launch_bounds__(128)
+p2p_scatter_rows_kernel(const uint16_t* __restrict__ src, int ld_src, const ScatterPeers peers, int ld_dst,
+                        int cols, int rows_per_peer) {
+  const int row = blockIdx.x;
+  const int d = row / rows_per_peer, r = row - d * rows_per_peer;
+  const uint4* s = reinterpret_cast<const uint4*>(src + static_cast<size_t>(row) * ld_src);
+  uint4* o = reinterpret_cast<uint4*>(peers.dst[d] + static_cast<size_t>(r) * ld_dst);
+  for (int vi = threadIdx.x; vi < (cols >> 3); vi += blockDim.x) o[vi] = s[vi];
+}
+
+int p2p_scatter_rows(const void* src, int ld_src, void* const* dst_peer, int ld_dst, int rows, int cols,
+                     int rows_per_peer, int world, cudaStream_t stream) {
+  if (world < 1 || world > 8 || cols % 8 != 0 || ld_src % 8 != 0 || ld_dst % 8 != 0 || rows <= 0 ||
+      rows_per_peer <= 0 || rows > rows_per_peer * world) {
+    set_last_error("p2p_scatter_rows: unsupported rows=%d cols=%d rows_per_peer=%d world=%d", rows, cols,
+                   rows_per_peer, world);
+    return KR_ERR_INVALID_ARG;
+  }
+  ScatterPeers sp;
+  for (int i = 0; i < 8; ++i) sp.dst[i] = i < world ? static_cast<uint16_t*>(dst_peer[i]) : nullptr;
+  p2p_scatter_rows_kernel<<<rows, 128, 0, stream>>>(static_cast<const uint16_t*>(src), ld_src, sp, ld_dst, cols,
+                                                    rows_per_peer);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("p2p_scatter_rows: launch failed: %s", cudaGetErrorString(e));
+    return KR_ERR_CUDA;
+  }
+  return KR_OK;
 }
 
 int qkv_post(const QkvPostParams& p, int rows, cudaStream_t stream) {

@@ -19,6 +19,7 @@
 // (2 x BLOCK_N fp32 columns) so the epilogue of tile i overlaps the mainloop of
 // tile i+1.
 #include "kr_common.cuh"
+#include "kr_gemm_epi.cuh"
 #include "kr_ops.h"
 
 #include <cstdlib>
@@ -188,93 +189,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias != nullptr) {
-            const uint4* b4 = reinterpret_cast<const uint4*>(
-                reinterpret_cast<const uint16_t*>(p.bias) + col0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 bb = __ldg(b4 + q);
-              uint32_t w[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                float2 f = kBf16 ? unpack_bf16x2(w[h]) : unpack_f16x2(w[h]);
-                v[q * 8 + h * 2] += f.x;
-                v[q * 8 + h * 2 + 1] += f.y;
-              }
-            }
-          }
-          if constexpr (kEpi == EPI_F32) {
-            float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldc + col0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float4 f4 = make_float4(v[q * 4] * p.alpha, v[q * 4 + 1] * p.alpha,
-                                      v[q * 4 + 2] * p.alpha, v[q * 4 + 3] * p.alpha);
-              reinterpret_cast<float4*>(o)[q] = f4;
-            }
-          } else {
-            auto rnd = [](float x) -> float {
-              return kBf16 ? __bfloat162float(__float2bfloat16_rn(x))
-                           : __half2float(__float2half_rn(x));
-            };
-            if constexpr (kEpi == EPI_BIAS_GELU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(rnd(v[j]));
-            }
-            if constexpr (kEpi == EPI_BIAS_GATE_RES) {
-              const uint4* g4 = reinterpret_cast<const uint4*>(gate_row + col0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint4 gg = __ldg(g4 + q);
-                uint32_t w[4] = {gg.x, gg.y, gg.z, gg.w};
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                  float2 f = kBf16 ? unpack_bf16x2(w[h]) : unpack_f16x2(w[h]);
-                  v[q * 8 + h * 2] = rnd(rnd(v[q * 8 + h * 2]) * f.x);
-                  v[q * 8 + h * 2 + 1] = rnd(rnd(v[q * 8 + h * 2 + 1]) * f.y);
-                }
-              }
-            }
-            if constexpr (kEpi == EPI_BIAS_GATE_RES || kEpi == EPI_BIAS_RES) {
-              const uint4* r4 = reinterpret_cast<const uint4*>(
-                  reinterpret_cast<const uint16_t*>(p.residual) + static_cast<size_t>(row) * p.ldr +
-                  col0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint4 rr = r4[q];
-                uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                  float2 f = kBf16 ? unpack_bf16x2(w[h]) : unpack_f16x2(w[h]);
-                  if constexpr (kEpi == EPI_BIAS_RES) {
-                    v[q * 8 + h * 2] = f.x + rnd(v[q * 8 + h * 2]);
-                    v[q * 8 + h * 2 + 1] = f.y + rnd(v[q * 8 + h * 2 + 1]);
-                  } else {
-                    v[q * 8 + h * 2] = f.x + v[q * 8 + h * 2];
-                    v[q * 8 + h * 2 + 1] = f.y + v[q * 8 + h * 2 + 1];
-                  }
-                }
-              }
-            }
-            uint16_t* o = (p.out2 != nullptr && col0 >= p.n_split)
-                ? reinterpret_cast<uint16_t*>(p.out2) + static_cast<size_t>(row) * p.ldc2 + (col0 - p.n_split)
-                : reinterpret_cast<uint16_t*>(p.out) + static_cast<size_t>(row) * p.ldc + col0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 w;
-              if (kBf16) {
-                w.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-                w.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-                w.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-                w.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-              } else {
-                w.x = pack_f16x2(v[q * 8 + 0], v[q * 8 + 1]);
-                w.y = pack_f16x2(v[q * 8 + 2], v[q * 8 + 3]);
-                w.z = pack_f16x2(v[q * 8 + 4], v[q * 8 + 5]);
-                w.w = pack_f16x2(v[q * 8 + 6], v[q * 8 + 7]);
-              }
-              reinterpret_cast<uint4*>(o)[q] = w;
-            }
-          }
+          gemm_epilogue_row32<kBf16, kEpi>(v, row, col0, p, gate_row);
         }
       }
       if (++acc == 2) {
@@ -353,8 +268,18 @@ static int dispatch_epi(int epi, const void* a, int lda, const void* w, int ldw,
 // to_qkv, 16.21 / 16.12 vs 16.23 / 16.26 fps in same-box bench runs -> not kept
 // (profiles/r01_gemm_hybrid_plan_*.log).
 // KR_GEMM2: 0 = never the pair kernel, 1 = by cost (default), 2 = pair whenever N % 256 == 0 (tests)
-int gemm_plan(int epi, int M, int N, int K) {
+int gemm_plan(int epi, int M, int N, int K, bool have_workspace) {
   static const int mode = [] { const char* e = getenv("KR_GEMM2"); return e != nullptr ? atoi(e) : 1; }();
+  // KR_GEMM_SK: 0 = never stream-K, 1 = when the data-parallel wave efficiency is poor (default)
+  static const int sk_mode = [] { const char* e = getenv("KR_GEMM_SK"); return e != nullptr ? atoi(e) : 1; }();
+  if (have_workspace && sk_mode > 0 && gemm_sk_preferred(epi, M, N, K)) {
+    // the CTA-pair kernel keeps shapes it fills well (its tiles are twice as large): pair waves vs stream-K
+    const int sms_ = sm_count(), pairs_ = sms_ / 2;
+    const long tp = static_cast<long>((M + 255) / 256) * (N / 256);
+    const double pair_eff = (mode > 0 && N % 256 == 0 && tp >= 4L * pairs_)
+        ? static_cast<double>(M) / 256.0 * (N / 256) / static_cast<double>(((tp + pairs_ - 1) / pairs_) * pairs_) : 0.0;
+    if (pair_eff < 0.80) return 2;
+  }
   if (mode <= 0 || epi == EPI_F32 || N % 256 != 0 || K < 256) return 0;
   if (mode == 2) return 1;
   const int sms = sm_count(), pairs = sms / 2, nb = N / 256;
@@ -365,7 +290,7 @@ int gemm_plan(int epi, int M, int N, int K) {
   const double cost_f = static_cast<double>((tiles_f + pairs - 1) / pairs);
   return cost_f < cost1 ? 1 : 0;
 }
-bool gemm_uses_pair(int epi, int M, int N, int K) { return gemm_plan(epi, M, N, K) != 0; }
+bool gemm_uses_pair(int epi, int M, int N, int K) { return gemm_plan(epi, M, N, K) == 1; }
 
 namespace {
 int gemm_single(int dtype, int epi, const void* a, int lda, const void* w, int ldw, const GemmParams& p,
@@ -402,7 +327,7 @@ int gemm_single(int dtype, int epi, const void* a, int lda, const void* w, int l
 }  // namespace
 
 int gemm_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, const GemmParams& p,
-            cudaStream_t stream) {
+            cudaStream_t stream, void* workspace, size_t workspace_bytes) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) {
     set_last_error("gemm: non-positive shape M=%d N=%d K=%d", p.M, p.N, p.K);
     return KR_ERR_INVALID_ARG;
@@ -424,7 +349,9 @@ int gemm_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, 
     set_last_error("gemm: gate epilogue without gate pointer / rows_per_gate");
     return KR_ERR_INVALID_ARG;
   }
-  const int plan = gemm_plan(epi, p.M, p.N, p.K);
+  const bool have_ws = workspace != nullptr && workspace_bytes >= gemm_sk_workspace_bytes();
+  const int plan = gemm_plan(epi, p.M, p.N, p.K, have_ws);
+  if (plan == 2) return gemm_sk_tn(dtype, epi, a, lda, w, ldw, p, workspace, workspace_bytes, stream);
   if (plan == 1) return gemm2_tn(dtype, epi, a, lda, w, ldw, p, stream);
   return gemm_single(dtype, epi, a, lda, w, ldw, p, stream);
 }

@@ -33,13 +33,19 @@ struct GemmParams {
   int ldc2;
   int n_split;
 };
+// workspace (optional): gemm_sk_workspace_bytes() bytes, zero-filled once, private to the stream -> enables the
+// stream-K kernel for shapes whose tile count leaves SMs idle (kr_gemm_sk.cu)
 int gemm_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, const GemmParams& p,
-            cudaStream_t stream);
+            cudaStream_t stream, void* workspace = nullptr, size_t workspace_bytes = 0);
+int gemm_sk_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, const GemmParams& p,
+               void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t gemm_sk_workspace_bytes();
+bool gemm_sk_preferred(int epi, int M, int N, int K);
 // CTA-pair (cta_group::2, 256x256 tiles) variant, kr_gemm2.cu
 int gemm2_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, const GemmParams& p,
              cudaStream_t stream);
 bool gemm_uses_pair(int epi, int M, int N, int K);
-int gemm_plan(int epi, int M, int N, int K);   // 0 single-CTA kernel, 1 CTA-pair kernel
+int gemm_plan(int epi, int M, int N, int K, bool have_workspace = false);   // 0 single-CTA kernel, 1 CTA-pair kernel, 2 stream-K
 
 struct AttnParams {
   void* out;           // [Lq, heads*128] 16-bit
@@ -75,8 +81,18 @@ struct QkvPostParams {
   int grid_h, grid_w, start_frame;
   int row_offset;                           // global token index of local row 0
   float eps;
+  // sequence-parallel exchange fused into the store (kr_comm, SURVEY.md 8e option 3): peer_cols > 0 sends the
+  // columns [d*peer_cols, (d+1)*peer_cols) (= the heads owned by rank d) of every row to rank d's buffers over
+  // NVLink peer memory instead of the local q_out / k_out / v_out.  The *_peer pointers address THIS rank's first
+  // row inside each destination buffer (row pitch ldqo / ldko / ldvo).
+  int peer_cols;
+  uint16_t* q_peer[8]; uint16_t* k_peer[8]; uint16_t* v_peer[8];
 };
 int qkv_post(const QkvPostParams& p, int rows, cudaStream_t stream);
+// rows [r*rows_per_peer, (r+1)*rows_per_peer) of src [rows, cols] -> peer r's buffer dst_peer[r] (pitch ld_dst):
+// the attention output of MY heads scattered back to the ranks that own the token rows
+int p2p_scatter_rows(const void* src, int ld_src, void* const* dst_peer, int ld_dst, int rows, int cols,
+                     int rows_per_peer, int world, cudaStream_t stream);
 int rmsnorm_rows(const void* x, int ldx, void* out, int ldo, const void* w, int rows, int D,
                  float eps, cudaStream_t stream);
 int add_modulation(const void* modulation, const void* e0, int lde0_frame, void* out, int frames,

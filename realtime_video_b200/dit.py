@@ -267,8 +267,40 @@ class CausalWanModel(nn.Module):
         if local_start < 0 or local_end > kv_size:
             raise RuntimeError(f"KV cache overflow: slot [{local_start}, {local_end}) of {kv_size}")
         k_slot, v_slot = kc[local_start:local_end], vc[local_start:local_end]
+        if sp is not None and sp.p2p:
+            # sequence-parallel, exchange done by the kernels: project MY rows (all heads); the RMSNorm+RoPE kernel
+            # stores every head's columns straight into the owning rank's q buffer / K slot / V slot over NVLink;
+            # after the barrier this rank attends ALL rows of ITS heads and scatters the output rows back
+            if sa.fused_projections:
+                qkv = ops.gemm(h, sa.to_qkv.weight, sa.to_qkv.bias)
+                q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+            else:
+                q = ops.gemm(h, sa.q.weight, sa.q.bias)
+                k = ops.gemm(h, sa.k.weight, sa.k.bias)
+                v = ops.gemm(h, sa.v.weight, sa.v.bias)
+            q_full, o_heads, o_rows = sp.exchange_buffers(L)
+            ops.qkv_norm_rope_p2p(q, k, v, sa.norm_q.weight, sa.norm_k.weight,
+                                  sp.peer_ptrs(q_full[r0:]), Dh, sp.peer_ptrs(k_slot[r0:]), Dh,
+                                  sp.peer_ptrs(v_slot[r0:]), Dh, sp.world, Dh, self._rope(h.device),
+                                  head_dim=sa.head_dim, grid_h=gh, grid_w=gw, start_frame=start_frame, eps=sa.eps,
+                                  row_offset=r0)
+            kv_cache["global_end_index"] = current_end
+            kv_cache["local_end_index"] = local_end
+            sp.barrier()
+            if mask is not None:
+                pad = math.ceil(L / 128) * 128 - L
+                ops.attention(q_full, kc[:L], vc[:L], heads=heads, block_len=mask.block_len, window=mask.window,
+                              pad_keys=pad, out=o_heads)
+            else:
+                max_att = sa._max_attention_frames * fs if sa.local_attn_size == -1 else sa.local_attn_size * fs
+                lo = max(0, local_end - max_att)
+                ops.attention(q_full, kc[lo:local_end], vc[lo:local_end], heads=heads, out=o_heads)
+            ops.comm_scatter_rows(o_heads, sp.peer_ptrs(o_rows[:, sp.rank * Dh:]), D, n_loc, sp.world)
+            sp.barrier()
+            return o_rows
         if sp is not None:
-            # sequence-parallel: project / normalise / rotate MY rows (all heads), then one
+            # sequence-parallel over torch.distributed collectives (NCCL baseline / gloo in the CPU tests): project
+            # / normalise / rotate MY rows (all heads), then one
             # all-to-all per tensor turns them into ALL rows of MY heads; K and V are received
             # straight into this rank's head-sharded cache slot
             if sa.fused_projections:

@@ -57,7 +57,23 @@ def profile_end() -> dict:
 
 
 # kr_gemm_kernel_id -> label used in the per-kernel timing split
-_GEMM_KERNELS = {1: "gemm_tn_kernel", 2: "gemm2_tn_kernel"}
+_GEMM_KERNELS = {1: "gemm_tn_kernel", 2: "gemm2_tn_kernel", 3: "gemm_sk_kernel"}
+
+# stream-K workspace (kr_gemm_ws): one zero-filled buffer per (device, stream), allocated on first use and
+# owned here (the library allocates nothing); set to False to force the data-parallel kernels
+stream_k = True
+_sk_ws = {}
+
+
+def _gemm_workspace(device: torch.device, stream: int):
+    if not stream_k:
+        return None, 0
+    key = (device.index, stream)
+    ws = _sk_ws.get(key)
+    if ws is None:
+        n = _lib.load().kr_gemm_workspace_bytes()
+        ws = _sk_ws[key] = torch.zeros(n, dtype=torch.uint8, device=device)
+    return ws.data_ptr(), ws.numel()
 
 
 class _Timed:
@@ -147,12 +163,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         _req(out2, "out2", a.dtype)
         _, ldc2 = _rows2d(out2, "out2")
     lib = _lib.load()
+    stream = _stream()
+    ws_ptr, ws_bytes = _gemm_workspace(a.device, stream)
     with _Timed("gemm", 2.0 * M * N * K,
-                sub=_GEMM_KERNELS[lib.kr_gemm_kernel_id(epilogue, M, N, K)] if _prof is not None else None):
-        rc = lib.kr_gemm(_DT[a.dtype], epilogue, a.data_ptr(), lda, w.data_ptr(), w.stride(0),
-                         _ptr(bias), out.data_ptr(), ldc, M, N, K, _ptr(residual), ldr, _ptr(gate), gs,
-                         rows_per_gate, alpha, _ptr(out2), ldc2, n_split, row_offset, _stream())
-    _lib.check(rc, "kr_gemm")
+                sub=_GEMM_KERNELS[lib.kr_gemm_kernel_id_ws(epilogue, M, N, K, 1 if ws_ptr else 0)]
+                if _prof is not None else None):
+        rc = lib.kr_gemm_ws(_DT[a.dtype], epilogue, a.data_ptr(), lda, w.data_ptr(), w.stride(0),
+                            _ptr(bias), out.data_ptr(), ldc, M, N, K, _ptr(residual), ldr, _ptr(gate), gs,
+                            rows_per_gate, alpha, _ptr(out2), ldc2, n_split, row_offset, ws_ptr, ws_bytes, stream)
+    _lib.check(rc, "kr_gemm_ws")
     _count()
     return out
 
@@ -230,6 +249,35 @@ def qkv_norm_rope(q, k, v, wq, wk, q_out, k_out, v_out, rope, *, head_dim: int, 
                               _ptr(v_out), ldvo, _ptr(rope), rows, D, head_dim, grid_h, grid_w,
                               start_frame, row_offset, eps, _stream())
     _lib.check(rc, "kr_qkv_norm_rope")
+    _count()
+
+
+def qkv_norm_rope_p2p(q, k, v, wq, wk, q_peers, ldqo: int, k_peers, ldko: int, v_peers, ldvo: int, world: int,
+                      peer_cols: int, rope, *, head_dim: int, grid_h: int, grid_w: int, start_frame: int,
+                      eps: float, row_offset: int = 0) -> None:
+    """``qkv_norm_rope`` whose stores are the rows->heads exchange of the multi-GPU mode: ``*_peers`` are ctypes
+    arrays of ``world`` device pointers (this rank's first row inside every rank's q buffer / K slot / V slot)."""
+    _req(q, "q", torch.bfloat16)
+    rows, ldq = _rows2d(q, "q")
+    _, ldk = _rows2d(k, "k")
+    _, ldv = _rows2d(v, "v")
+    lib = _lib.load()
+    rc = lib.kr_qkv_norm_rope_p2p(q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, wq.data_ptr(),
+                                  wk.data_ptr(), q_peers, ldqo, k_peers, ldko, v_peers, ldvo, world, peer_cols,
+                                  _ptr(rope), rows, q.shape[-1], head_dim, grid_h, grid_w, start_frame,
+                                  row_offset, eps, _stream())
+    _lib.check(rc, "kr_qkv_norm_rope_p2p")
+    _count()
+
+
+def comm_scatter_rows(src: torch.Tensor, dst_peers, ld_dst: int, rows_per_peer: int, world: int) -> None:
+    """rows [r*rows_per_peer, ...) of ``src`` [rows, cols] -> rank r's buffer ``dst_peers[r]`` (row pitch ld_dst)."""
+    _req(src, "src")
+    rows, ld = _rows2d(src, "src")
+    lib = _lib.load()
+    rc = lib.kr_comm_scatter_rows(src.data_ptr(), ld, dst_peers, ld_dst, rows, src.shape[-1], rows_per_peer, world,
+                                  _stream())
+    _lib.check(rc, "kr_comm_scatter_rows")
     _count()
 
 

@@ -1,22 +1,34 @@
-"""Single-stream multi-GPU mode: Ulysses-style sequence parallelism for the DiT block stack.
+"""Single-stream multi-GPU mode: Ulysses-style sequence parallelism for the DiT block stack (SURVEY.md §8e opt. 3).
 
-The hot path is ONE strictly sequential stream (B=1; every pass needs the previous one), so it does
-not shard into independent units; ``bench.py --gpus N`` therefore defaults to
-independent replicas.  This module is the latency-oriented alternative: all N GPUs work on the
-same block.
+The hot path is ONE strictly sequential stream (B=1; every pass needs the previous one), so it does not shard
+into independent units.  Here all N GPUs of a box work on the same block:
 
-  * token rows are sharded contiguously (L/N rows per rank) for everything token-wise:
-    LayerNorm/modulation, QKV / o / cross-attention / FFN GEMMs, RMSNorm+RoPE — weights replicated;
-  * self-attention is sharded by HEAD (heads/N per rank, full sequence): one all-to-all turns
-    row-sharded q/k/v [L/N, heads*128] into head-sharded [L, heads/N*128] (K and V land directly
-    in the rank's head-sharded KV-cache slot), a second one brings the attention output back;
-  * per layer and rank that is 4 x (L/N x 5120) bf16 out and in (21 MB at N=8) over NVLink.
-The collectives are torch.distributed all_to_all_single / all_gather (NCCL on GPUs; gloo in the
-CPU tests).  Results are bit-identical to the single-GPU path: every kernel computes each output
-row / head exactly as before, only the placement changes (tests/test_parallel.py).
+  * token rows are sharded contiguously (L/N rows per rank) for everything token-wise: LayerNorm/modulation,
+    QKV / o / cross-attention / FFN GEMMs (stream-K kernel: an L/N-row GEMM has too few tiles for 148 SMs),
+    RMSNorm+RoPE — weights replicated (28 GB of 180 GB);
+  * self-attention is sharded by HEAD (heads/N per rank, full sequence).
+
+Two exchange back ends:
+
+``p2p`` (GPUs, default): the exchange is done BY THE KERNELS over NVLink peer memory.  Every rank owns one
+    symmetric allocation (torch.distributed._symmetric_memory: rendezvous hands out the peers' addresses; torch is
+    plumbing) holding its head-sharded q buffer, its head-sharded KV caches and its row-sharded attention-output
+    buffer.  ``kr_qkv_norm_rope_p2p`` (RMSNorm + RoPE of my rows) stores each head's columns straight into the
+    owning rank's q buffer / K-cache slot / V-cache slot; after the attention ``kr_comm_scatter_rows`` stores my
+    heads' output rows into the owners' row buffers.  Per layer: two device-side barriers (symmetric-memory signal
+    pads) instead of four NCCL all-to-alls and their pack / unpack copies.
+    Buffer reuse is safe with exactly these two barriers: a rank passes barrier A(l+1) only after its own o-proj(l)
+    read its row buffer, and passes barrier B(l) only after every rank's attention(l) has read its q buffer.
+``nccl`` (and gloo in the CPU tests): torch.distributed all_to_all_single with pack / unpack copies — the
+    baseline the p2p path is measured against, and the host-logic reference for tests/test_parallel.py.
+
+Every kernel computes each output row / head exactly as on one GPU; only the placement changes.  (The stream-K
+GEMM sums split-K partials in a different order than the data-parallel kernel: results agree to fp32 rounding of
+the accumulator, not bit for bit.)
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Optional
 
 import torch
@@ -24,12 +36,23 @@ import torch.distributed as dist
 
 
 class SequenceParallel:
-    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, group: Optional[dist.ProcessGroup] = None, exchange: Optional[str] = None):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised before SequenceParallel()")
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        if exchange is None:
+            exchange = "p2p" if dist.get_backend(group) == "nccl" else "nccl"
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError(exchange)
+        self.exchange = exchange
+        self._arena = None           # symmetric allocation (uint8)
+        self._hdl = None
+        self._peer_base = None
+        self._used = 0
+        self._ptr_cache = {}
+        self._kv = self._kv_key = self._q_buf = self._o_rows_buf = self._o_heads_buf = None
 
     # -- sharding arithmetic -------------------------------------------------------------------
     def rows(self, L: int):
@@ -44,7 +67,89 @@ class SequenceParallel:
             raise ValueError(f"{heads} heads are not divisible by {self.world} ranks")
         return heads // self.world
 
-    # -- collectives ---------------------------------------------------------------------------
+    # -- p2p back end: symmetric arena ---------------------------------------------------------
+    @property
+    def p2p(self) -> bool:
+        return self.exchange == "p2p"
+
+    def reserve(self, nbytes: int, device) -> None:
+        """Create the symmetric arena (once; collective).  Sized by the caller for: KV caches + q / o buffers."""
+        if self._arena is not None:
+            if self._arena.numel() < nbytes:
+                raise RuntimeError("symmetric arena already created with a smaller size")
+            return
+        import torch.distributed._symmetric_memory as symm_mem
+        g = self.group if self.group is not None else dist.group.WORLD
+        self._arena = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        self._hdl = symm_mem.rendezvous(self._arena, g.group_name)
+        self._peer_base = [int(p) for p in self._hdl.buffer_ptrs]
+        assert self._peer_base[self.rank] == self._arena.data_ptr()
+        self._used = 0
+
+    def carve(self, shape, dtype) -> torch.Tensor:
+        """A tensor inside the arena; every rank must carve the same sequence of shapes (same offsets)."""
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        off = (self._used + 255) // 256 * 256
+        if off + nbytes > self._arena.numel():
+            raise RuntimeError(f"symmetric arena exhausted: need {off + nbytes} of {self._arena.numel()} bytes")
+        self._used = off + nbytes
+        return self._arena[off:off + nbytes].view(dtype).view(*shape)
+
+    def peer_ptrs(self, t: torch.Tensor, byte_offset_of=None):
+        """ctypes array of world pointers: the address of ``t``'s first element in every rank's arena."""
+        key = t.data_ptr()
+        arr = self._ptr_cache.get(key)
+        if arr is None:
+            off = key - self._arena.data_ptr()
+            if off < 0 or off >= self._arena.numel():
+                raise RuntimeError("tensor is not inside the symmetric arena")
+            arr = (ctypes.c_void_p * self.world)(*[b + off for b in self._peer_base])
+            if len(self._ptr_cache) > 4096:
+                self._ptr_cache.clear()
+            self._ptr_cache[key] = arr
+        return arr
+
+    def barrier(self) -> None:
+        """Device-side barrier on the current stream (symmetric-memory signal pads): all ranks' earlier kernels —
+        including their remote stores into this rank's arena — are complete and visible afterwards."""
+        self._hdl.barrier(channel=0)
+
+    def alloc_kv_cache(self, num_layers: int, shape, dtype, device):
+        """KV caches [1, rows, heads_local, head_dim] x 2 x layers plus the exchange buffers, all inside ONE symmetric
+        allocation created here (collective, once per object).  Returns [(k, v)] per layer, zero-filled."""
+        key = (num_layers, tuple(int(d) for d in shape), dtype)
+        if self._arena is None:
+            rows, hl, hd = key[1][1], key[1][2], key[1][3]
+            es = torch.empty((), dtype=dtype).element_size()
+            dh, D = hl * hd, hl * hd * self.world
+
+            def al(n):
+                return (n + 255) // 256 * 256
+            n_loc = rows // self.world + 8
+            self.reserve(2 * num_layers * al(rows * dh * es) + al(rows * dh * es) + al(n_loc * D * es) + 4096, device)
+            self._kv = [(self.carve(key[1], dtype), self.carve(key[1], dtype)) for _ in range(num_layers)]
+            self._q_buf = self.carve((rows, dh), dtype)                 # all rows, my heads (peers write)
+            self._o_rows_buf = self.carve((n_loc, D), dtype)            # my rows, all heads (peers write)
+            self._o_heads_buf = torch.empty(rows, dh, dtype=dtype, device=device)     # local attention output
+            self._kv_key = key
+        elif self._kv_key != key:
+            raise RuntimeError(f"SequenceParallel holds a KV cache of geometry {self._kv_key}; asked for {key}")
+        for k, v in self._kv:
+            k.zero_()
+            v.zero_()
+        return self._kv
+
+    def exchange_buffers(self, L: int):
+        """q_full [L, D/N] (all rows, my heads), o_heads [L, D/N] (local), o_rows [L/N, D] (my rows, all heads)."""
+        if self._arena is None or L > self._q_buf.shape[0]:
+            raise RuntimeError("exchange buffers are sized with the KV cache: allocate it through alloc_kv_cache "
+                               "(harness PipelineState does) before the first forward")
+        return self._q_buf[:L], self._o_heads_buf[:L], self._o_rows_buf[:L // self.world]
+
+    # -- nccl / gloo back end ------------------------------------------------------------------
     def rows_to_heads(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """x [L/N, H*128] (my rows, all heads) -> [L, H/N*128] (all rows in global order, my heads).
         ``out`` may be a row-contiguous view (e.g. a KV-cache slot) that receives the result."""
