@@ -59,6 +59,7 @@ class Models:
 
 
 class GenerationSession:
+    @torch.inference_mode()          # like the reference (release_server.py:347): the caches it resets are inference tensors
     def __init__(self, params: GenerateParams, models: Models, prompt_embeds: Optional[torch.Tensor] = None,
                  device=None, decode: bool = True):
         self.params, self.models, self.decode = params, models, decode

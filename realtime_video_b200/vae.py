@@ -454,6 +454,35 @@ class DecoderEngine:
 
 
 # ---------------------------------------------------------------------------------------------
+# torch.compile boundary: one opaque op per streaming decode (pattern: wan/modules/sage.py:12-19)
+# ---------------------------------------------------------------------------------------------
+_DECODERS: dict = {}
+
+
+def _register_decoder(mod) -> int:
+    import weakref
+    h = len(_DECODERS) + 1
+    _DECODERS[h] = weakref.ref(mod)
+    return h
+
+
+@torch.library.custom_op("krea_b200::vae_decode_stream", mutates_args=())
+def _vae_decode_stream(z: torch.Tensor, first: bool, handle: int) -> List[torch.Tensor]:
+    mod = _DECODERS[handle]()
+    px, _ = mod._decode(z, [None] * 55 if first else mod.engine.export_cache())
+    mod._stream_calls = getattr(mod, "_stream_calls", 0) + 1
+    return [px, torch.full((1,), mod._stream_calls, dtype=torch.int64, device=z.device)]
+
+
+@_vae_decode_stream.register_fake
+def _(z, first, handle):
+    t = z.shape[1]
+    frames = 4 * t - 3 if first else 4 * t
+    return [z.new_empty((1, frames, 3, z.shape[-2] * 8, z.shape[-1] * 8), dtype=torch.float32),
+            z.new_empty((1,), dtype=torch.int64)]
+
+
+# ---------------------------------------------------------------------------------------------
 # the reference-facing wrappers
 # ---------------------------------------------------------------------------------------------
 class VAEDecoderWrapper(nn.Module):
@@ -469,6 +498,12 @@ class VAEDecoderWrapper(nn.Module):
         self.z_dim = 16
         self.conv2 = CausalConv3d(self.z_dim, self.z_dim, 1)
         self._engine: Optional[DecoderEngine] = None
+        self._handle = _register_decoder(self)      # id of this module for the opaque torch.compile op
+
+    def __setstate__(self, state):                  # deepcopy / unpickle (release_server.py:111-119): own handle, own engine
+        super().__setstate__(state)
+        self._engine = None
+        self._handle = _register_decoder(self)
 
     @property
     def engine(self) -> DecoderEngine:
@@ -480,10 +515,23 @@ class VAEDecoderWrapper(nn.Module):
         self._engine = None
         return super()._apply(fn, *a, **k)
 
-    def forward(self, z: torch.Tensor, *feat_cache):
+    def _decode(self, z: torch.Tensor, feat_cache):
         eng = self.engine
         eng.mean, eng.std = self.mean, self.std
-        return eng.decode(z, list(feat_cache))
+        return eng.decode(z, feat_cache)
+
+    def forward(self, z: torch.Tensor, *feat_cache):
+        if torch.compiler.is_compiling():
+            # torch.compile(vae_decoder, fullgraph=True) (release_server.py:754): the whole streaming decode is ONE
+            # opaque custom op; the feature cache stays inside the engine and the caller gets a 55-entry list whose
+            # first entry is a stream token (all-None = new stream, exactly like the eager convention)
+            first = all(c is None for c in feat_cache)
+            px, token = torch.ops.krea_b200.vae_decode_stream(z, first, self._handle)
+            return px, [token] + [None] * 54
+        cache = list(feat_cache)
+        if cache and cache[0] is not None and cache[0].dtype == torch.int64:      # token from a compiled call
+            cache = self.engine.export_cache()
+        return self._decode(z, cache)
 
 
 class VAEDecoderWrapperSingle(nn.Module):
@@ -505,6 +553,7 @@ class VAEDecoderWrapperSingle(nn.Module):
         self._engine = None
         return super()._apply(fn, *a, **k)
 
+    @torch.compiler.disable
     def forward(self, z: torch.Tensor, is_first_frame: torch.Tensor, *feat_cache):
         if self._engine is None:
             self._engine = DecoderEngine(self.decoder, self.conv2, self.mean, self.std, single_mode=True)
@@ -767,6 +816,7 @@ class VAEEncoderWrapper(nn.Module):
         self._engine = None
         return super()._apply(fn, *a, **k)
 
+    @torch.compiler.disable
     def forward(self, z: torch.Tensor, feat_cache, stream: bool = False):
         if z.shape[0] != 1:
             raise NotImplementedError("B200 VAE encoder: batch size 1 (as every call site of the reference)")

@@ -220,6 +220,10 @@ class WanDiffusionWrapper(nn.Module):
         return ((xt.double() - x0_pred.double()) / sig[idx].reshape(-1, 1, 1, 1)).to(dt)
 
     # -- utils/wan_wrapper.py:230-301 ---------------------------------------------------------
+    # The server may wrap this module in torch.compile (release_server.py:753-755, DO_COMPILE=true).  The pass is a
+    # fixed, hand-fused schedule of C-ABI launches: there is nothing for a tracing compiler to fuse, so the frame is
+    # marked opaque — torch.compile(module) returns a module that runs this forward eagerly (tests/test_compile_cpu.py).
+    @torch.compiler.disable
     def forward(self, noisy_image_or_video: torch.Tensor, conditional_dict: dict,
                 timestep: torch.Tensor, kv_cache: Optional[List[dict]] = None,
                 crossattn_cache: Optional[List[dict]] = None, current_start: Optional[int] = None,

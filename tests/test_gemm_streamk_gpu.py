@@ -20,6 +20,7 @@ def _case(M, N, K, epi, repeats=3):
     w = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
     b = torch.randn(N, device="cuda").bfloat16()
     ref = a.float() @ w.float().t() + b.float()
+    gate = torch.randn(3, N, device="cuda").bfloat16()
     outs = []
     for _ in range(repeats):
         if epi == "bias":
@@ -29,7 +30,6 @@ def _case(M, N, K, epi, repeats=3):
             want = torch.nn.functional.gelu(ref.bfloat16().float(), approximate="tanh")
         elif epi == "gate_res":
             x = torch.ones(M, N, device="cuda").bfloat16()
-            gate = torch.randn(3, N, device="cuda").bfloat16()
             rpg = (M + 2) // 3
             rows = torch.arange(M, device="cuda") // rpg
             want = x.float() + (ref.bfloat16().float() * gate.float()[rows]).bfloat16().float()
