@@ -42,6 +42,7 @@ const char* kr_last_error(void);
 #define KR_EPI_BIAS_GATE_RES 2 /* out = cast(res + cast(cast(acc+bias) * gate[row/rows_per_gate])) */
 #define KR_EPI_BIAS_RES 3      /* out = cast(res + cast(acc + bias))                             */
 #define KR_EPI_F32 4           /* out(fp32) = (acc + bias) * alpha                               */
+#define KR_EPI_MUL 5           /* out = cast(cast(acc + bias) * res)  (UMT5 gated FFN, t5.py:138-140) */
 
 /* out[M,N] = epilogue(a[M,K] @ w[N,K]^T + bias[N]); tcgen05/TMEM tensor-core GEMM.
  * Replaces nn.Linear (cuBLASLt) + the elementwise ops that follow it:
@@ -89,6 +90,14 @@ int kr_attn_fwd(int dtype, const void* q, int ldq, const void* k, int ldk, const
                 void* out, int ldo, int Lq, int Lkv, int heads, float softmax_scale, int mask_mode,
                 int block_len, int window, int pad_keys, void* stream);
 
+/* UMT5 encoder self-attention, one launch per layer: head_dim 64, bf16, L <= 1024, no 1/sqrt(d) scaling;
+ *   out[q,h,:] = softmax_k( bf16(bf16(q.k) + bias_delta[h, k - q + L-1]) ) v[k,h,:],  masked keys (key_mask[k] == 0)
+ * get finfo(bf16).min like the reference.  bias_delta [heads, 2L-1] bf16 = the layer's relative-position embedding
+ * gathered by offset (T5RelativeEmbedding, wan/modules/t5.py:221-264); key_mask [L] uint8 or NULL.
+ * Replaces T5Attention.forward's einsum / bias / fp32 softmax / einsum (wan/modules/t5.py:86-120). */
+int kr_t5_attn(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int L,
+               int heads, const void* bias_delta, const void* key_mask, void* stream);
+
 /* WanLayerNorm (+affine) (+per-frame modulation x*(1+scale)+shift).
  * mod: [frames, mod_rows, D] 16-bit or NULL; w,b: [D] or NULL.
  * Replaces wan/modules/model.py:88-98 + causal_model.py:466-471, :482-485, :520-522 (bf16). */
@@ -121,6 +130,11 @@ int kr_qkv_norm_rope_p2p(const void* q, int ldq, const void* k, int ldk, const v
                          float eps, void* stream);
 int kr_comm_scatter_rows(const void* src, int ld_src, void* const* dst_peer, int ld_dst, int rows, int cols,
                          int rows_per_peer, int world, void* stream);
+
+/* Rolling-window eviction of the self-attention KV cache (causal_model.py:363-373: `cache[sink : sink+rolled] =
+ * cache[sink+evicted : sink+evicted+rolled].clone()`): rows [src_row, src_row+rows) of a 16-bit [*, ld] cache move
+ * down to [dst_row, ...) in place (ranges may overlap, dst_row <= src_row), only the first `width` columns. */
+int kr_kv_roll(void* cache, int ld, int width, int dst_row, int src_row, int rows, void* stream);
 
 /* WanRMSNorm rows (cross-attention q / k): model.py:69-85, :183-190 */
 int kr_rmsnorm(const void* x, int ldx, void* out, int ldo, const void* w, int rows, int D,

@@ -16,7 +16,7 @@ from pathlib import Path
 _PKG_DIR = Path(__file__).resolve().parent
 _CSRC = _PKG_DIR / "csrc"
 LIB_PATH = _PKG_DIR / "libkrea_b200.so"
-SOURCES = ["kr_host.cu", "kr_gemm.cu", "kr_gemm2.cu", "kr_gemm_sk.cu", "kr_attn.cu", "kr_dit_elem.cu", "kr_vae.cu", "kr_api.cu"]
+SOURCES = ["kr_host.cu", "kr_gemm.cu", "kr_gemm2.cu", "kr_gemm_sk.cu", "kr_attn.cu", "kr_t5attn.cu", "kr_dit_elem.cu", "kr_vae.cu", "kr_api.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -98,12 +98,14 @@ SIGNATURES = {
     "kr_gemm": [_i, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _f, _vp, _i, _i,
                 _i, _vp],
     "kr_attn_fwd": [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _f, _i, _i, _i, _i, _vp],
+    "kr_t5_attn": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp],
     "kr_ln_modulate": [_vp, _i, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "kr_qkv_norm_rope": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i,
                          _i, _i, _i, _i, _i, _i, _f, _vp],
     "kr_qkv_norm_rope_p2p": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp,
                              _i, _i, _i, _i, _i, _i, _i, _f, _vp],
     "kr_comm_scatter_rows": [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
+    "kr_kv_roll": [_vp, _i, _i, _i, _i, _i, _vp],
     "kr_rmsnorm": [_vp, _i, _vp, _i, _vp, _i, _i, _f, _vp],
     "kr_add_modulation": [_vp, _vp, _i, _vp, _i, _i, _i, _vp],
     "kr_activation": [_vp, _vp, _sz, _i, _vp],

@@ -61,6 +61,14 @@ int kr_attn_fwd(int dtype, const void* q, int ldq, const void* k, int ldk, const
   return kr::attn_fwd(dtype, q, ldq, k, ldk, v, ldv, p, static_cast<cudaStream_t>(stream));
 }
 
+int kr_t5_attn(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int L,
+               int heads, const void* bias_delta, const void* key_mask, void* stream) {
+  KR_REQUIRE(q && k && v && out && bias_delta, "null q/k/v/out/bias");
+  kr::T5AttnParams p;
+  p.out = out; p.ldo = ldo; p.L = L; p.heads = heads; p.bias_delta = bias_delta; p.key_mask = key_mask;
+  return kr::t5_attn(q, ldq, k, ldk, v, ldv, p, static_cast<cudaStream_t>(stream));
+}
+
 int kr_ln_modulate(const void* x, int ldx, void* out, int ldo, int rows, int D, float eps,
                    const void* w, const void* b, const void* mod, int mod_rows, int shift_idx,
                    int scale_idx, int rows_per_frame, int row_offset, void* stream) {
@@ -125,6 +133,11 @@ int kr_comm_scatter_rows(const void* src, int ld_src, void* const* dst_peer, int
   KR_REQUIRE(src && dst_peer, "null src / peer table");
   return kr::p2p_scatter_rows(src, ld_src, dst_peer, ld_dst, rows, cols, rows_per_peer, world,
                               static_cast<cudaStream_t>(stream));
+}
+
+int kr_kv_roll(void* cache, int ld, int width, int dst_row, int src_row, int rows, void* stream) {
+  KR_REQUIRE(cache, "null cache");
+  return kr::kv_roll(cache, ld, width, dst_row, src_row, rows, static_cast<cudaStream_t>(stream));
 }
 
 int kr_rmsnorm(const void* x, int ldx, void* out, int ldo, const void* w, int rows, int D,

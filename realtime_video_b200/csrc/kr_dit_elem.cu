@@ -283,6 +283,48 @@ __global__ void __launch_bounds__(kRowThreads, 6) qkv_post_kernel(const QkvPostP
 }
 
 // ---------------------------------------------------------------------------
+// KV-cache roll (rolling-window eviction, causal_model.py:363-373): rows [src_row, src_row + rows) move down to
+// [dst_row, dst_row + rows), dst_row < src_row, ranges may overlap.  The reference does it with a `.clone()` of
+// the whole window per tensor; here every thread owns ONE 16-byte column of the row and walks the rows in
+// ascending order (reads of a batch of rows precede the writes of that batch), so an overlapping shift needs no
+// temporary and no ordering between threads: a column is only ever touched by its own thread.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+kv_roll_kernel(uint4* __restrict__ base, long pitch_vec, int vecs_per_row, int dst_row, int src_row, int rows) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= vecs_per_row) return;
+  constexpr int U = 8;
+  uint4* d = base + static_cast<size_t>(dst_row) * pitch_vec + col;
+  const uint4* s = base + static_cast<size_t>(src_row) * pitch_vec + col;
+  int r = 0;
+  for (; r + U <= rows; r += U) {
+    uint4 t[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) t[j] = s[static_cast<size_t>(r + j) * pitch_vec];
+#pragma unroll
+    for (int j = 0; j < U; ++j) d[static_cast<size_t>(r + j) * pitch_vec] = t[j];
+  }
+  for (; r < rows; ++r) d[static_cast<size_t>(r) * pitch_vec] = s[static_cast<size_t>(r) * pitch_vec];
+}
+
+int kv_roll(void* cache, int ld, int width, int dst_row, int src_row, int rows, cudaStream_t stream) {
+  if (ld % 8 != 0 || width % 8 != 0 || width > ld || rows < 0 || dst_row < 0 || src_row < dst_row) {
+    set_last_error("kv_roll: unsupported ld=%d width=%d dst=%d src=%d rows=%d", ld, width, dst_row, src_row, rows);
+    return KR_ERR_INVALID_ARG;
+  }
+  if (rows == 0 || src_row == dst_row) return KR_OK;
+  const int vecs = width / 8;
+  kv_roll_kernel<<<(vecs + 255) / 256, 256, 0, stream>>>(static_cast<uint4*>(cache), ld / 8, vecs, dst_row, src_row,
+                                                         rows);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("kv_roll: launch failed: %s", cudaGetErrorString(e));
+    return KR_ERR_CUDA;
+  }
+  return KR_OK;
+}
+
+// ---------------------------------------------------------------------------
 // rows of src -> the peer that owns them (attention output back from head-sharded to row-sharded)
 // ---------------------------------------------------------------------------
 struct ScatterPeers { uint16_t* dst[8]; };

@@ -252,6 +252,7 @@ static int dispatch_epi(int epi, const void* a, int lda, const void* w, int ldw,
       return launch_gemm<BLOCK_N, kBf16, EPI_BIAS_GATE_RES>(a, lda, w, ldw, p, s);
     case EPI_BIAS_RES: return launch_gemm<BLOCK_N, kBf16, EPI_BIAS_RES>(a, lda, w, ldw, p, s);
     case EPI_F32: return launch_gemm<BLOCK_N, kBf16, EPI_F32>(a, lda, w, ldw, p, s);
+    case EPI_MUL: return launch_gemm<BLOCK_N, kBf16, EPI_MUL>(a, lda, w, ldw, p, s);
     default: set_last_error("gemm: unknown epilogue %d", epi); return KR_ERR_INVALID_ARG;
   }
 }
@@ -280,7 +281,7 @@ int gemm_plan(int epi, int M, int N, int K, bool have_workspace) {
         ? static_cast<double>(M) / 256.0 * (N / 256) / static_cast<double>(((tp + pairs_ - 1) / pairs_) * pairs_) : 0.0;
     if (pair_eff < 0.80) return 2;
   }
-  if (mode <= 0 || epi == EPI_F32 || N % 256 != 0 || K < 256) return 0;
+  if (mode <= 0 || epi == EPI_F32 || epi == EPI_MUL || N % 256 != 0 || K < 256) return 0;
   if (mode == 2) return 1;
   const int sms = sm_count(), pairs = sms / 2, nb = N / 256;
   const long tiles1 = static_cast<long>((M + 127) / 128) * nb;
@@ -337,7 +338,7 @@ int gemm_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, 
                    p.M, p.N, p.K);
     return KR_ERR_UNSUPPORTED_SHAPE;
   }
-  if ((epi == EPI_BIAS_GATE_RES || epi == EPI_BIAS_RES) && p.residual == nullptr) {
+  if ((epi == EPI_BIAS_GATE_RES || epi == EPI_BIAS_RES || epi == EPI_MUL) && p.residual == nullptr) {
     set_last_error("gemm: residual epilogue without residual pointer");
     return KR_ERR_INVALID_ARG;
   }

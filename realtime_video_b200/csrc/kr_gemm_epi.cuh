@@ -58,7 +58,7 @@ KR_DEVICE void gemm_epilogue_row32(float (&v)[32], const int row, const int col0
           }
         }
       }
-      if constexpr (kEpi == EPI_BIAS_GATE_RES || kEpi == EPI_BIAS_RES) {
+      if constexpr (kEpi == EPI_BIAS_GATE_RES || kEpi == EPI_BIAS_RES || kEpi == EPI_MUL) {
         const uint4* r4 = reinterpret_cast<const uint4*>(
             reinterpret_cast<const uint16_t*>(p.residual) + static_cast<size_t>(row) * p.ldr +
             col0);
@@ -69,7 +69,10 @@ KR_DEVICE void gemm_epilogue_row32(float (&v)[32], const int row, const int col0
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
             float2 f = kBf16 ? unpack_bf16x2(w[h]) : unpack_f16x2(w[h]);
-            if constexpr (kEpi == EPI_BIAS_RES) {
+            if constexpr (kEpi == EPI_MUL) {
+            v[q * 8 + h * 2] = f.x * rnd(v[q * 8 + h * 2]);
+            v[q * 8 + h * 2 + 1] = f.y * rnd(v[q * 8 + h * 2 + 1]);
+          } else if constexpr (kEpi == EPI_BIAS_RES) {
               v[q * 8 + h * 2] = f.x + rnd(v[q * 8 + h * 2]);
               v[q * 8 + h * 2 + 1] = f.y + rnd(v[q * 8 + h * 2 + 1]);
             } else {

@@ -348,6 +348,7 @@ int gemm_sk_tn(int dtype, int epi, const void* a, int lda, const void* w, int ld
     case EPI_BIAS_GELU: return KR_SK(EPI_BIAS_GELU);
     case EPI_BIAS_GATE_RES: return KR_SK(EPI_BIAS_GATE_RES);
     case EPI_BIAS_RES: return KR_SK(EPI_BIAS_RES);
+    case EPI_MUL: return KR_SK(EPI_MUL);
     default: set_last_error("gemm_sk: unsupported epilogue %d", epi); return KR_ERR_INVALID_ARG;
   }
 #undef KR_SK

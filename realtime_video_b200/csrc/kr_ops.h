@@ -13,6 +13,7 @@ enum GemmEpilogue : int {
   EPI_BIAS_GATE_RES = 2,  // out = cast(res + cast(cast(acc + bias) * gate[row / rows_per_gate]))
   EPI_BIAS_RES = 3,       // out = cast(res + cast(acc + bias))
   EPI_F32 = 4,            // out(fp32) = (acc + bias) * alpha
+  EPI_MUL = 5,            // out = cast(cast(acc + bias) * res)   (gated FFN: fc1(x) * gelu(gate(x)), t5.py:138-140)
 };
 
 struct GemmParams {
@@ -65,6 +66,16 @@ struct AttnParams {
 int attn_fwd(int dtype, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
              const AttnParams& p, cudaStream_t stream);
 
+// UMT5 self-attention (kr_t5attn.cu): head_dim 64, bf16, bias by (head, k - q), key mask, no scaling
+struct T5AttnParams {
+  void* out; int ldo;            // [L, heads*64] bf16
+  int L, heads;
+  const void* bias_delta;        // [heads, 2L-1] bf16: entry d = position bias of relative offset k - q = d - (L-1)
+  const void* key_mask;          // [L] uint8 (1 = token, 0 = padding) or null
+};
+int t5_attn(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const T5AttnParams& p,
+            cudaStream_t stream);
+
 int ln_modulate(const void* x, int ldx, void* out, int ldo, int rows, int D, float eps,
                 const void* w, const void* b, const void* mod, int mod_rows, int shift_idx,
                 int scale_idx, int rows_per_frame, int row_offset, cudaStream_t stream);
@@ -93,6 +104,8 @@ int qkv_post(const QkvPostParams& p, int rows, cudaStream_t stream);
 // the attention output of MY heads scattered back to the ranks that own the token rows
 int p2p_scatter_rows(const void* src, int ld_src, void* const* dst_peer, int ld_dst, int rows, int cols,
                      int rows_per_peer, int world, cudaStream_t stream);
+// in-place downward shift of cache rows (16-bit elements): [src_row, src_row+rows) -> [dst_row, ...), dst_row <= src_row
+int kv_roll(void* cache, int ld, int width, int dst_row, int src_row, int rows, cudaStream_t stream);
 int rmsnorm_rows(const void* x, int ldx, void* out, int ldo, const void* w, int rows, int D,
                  float eps, cudaStream_t stream);
 int add_modulation(const void* modulation, const void* e0, int lde0_frame, void* out, int frames,

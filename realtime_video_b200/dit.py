@@ -258,8 +258,7 @@ class CausalWanModel(nn.Module):
                 evicted = L + l_end - kv_size
                 rolled = l_end - evicted - sink_tokens
                 for c in (kc, vc):      # left-shift the window, keeping the sink tokens (:363-373)
-                    c[sink_tokens:sink_tokens + rolled] = \
-                        c[sink_tokens + evicted:sink_tokens + evicted + rolled].clone()
+                    ops.kv_roll(c, sink_tokens, sink_tokens + evicted, rolled)
                 local_end = l_end + current_end - g_end - evicted
             else:
                 local_end = l_end + current_end - g_end

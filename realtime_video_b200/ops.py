@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES, EPI_BIAS_RES, EPI_F32 = 0, 1, 2, 3, 4
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES, EPI_BIAS_RES, EPI_F32, EPI_MUL = 0, 1, 2, 3, 4, 5
 
 _DT = {torch.bfloat16: 0, torch.float16: 1}
 
@@ -204,6 +204,31 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, heads: int,
     return out
 
 
+def t5_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bias_delta: torch.Tensor,
+                 key_mask: Optional[torch.Tensor], *, heads: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """UMT5 self-attention, head_dim 64: q/k/v [L, heads*64] bf16, bias_delta [heads, 2L-1] bf16 (position bias by
+    offset k - q), key_mask [L] uint8 or None -> [L, heads*64] (wan/modules/t5.py:86-120 in one launch)."""
+    _req(q, "q", torch.bfloat16); _req(k, "k", torch.bfloat16); _req(v, "v", torch.bfloat16)
+    _req(bias_delta, "bias_delta", torch.bfloat16)
+    L, ldq = _rows2d(q, "q")
+    _, ldk = _rows2d(k, "k")
+    _, ldv = _rows2d(v, "v")
+    if q.shape[-1] != heads * 64 or tuple(bias_delta.shape) != (heads, 2 * L - 1) or not bias_delta.is_contiguous():
+        raise _lib.KreaB200Error("t5_attention: need head_dim 64 and a contiguous bias_delta [heads, 2L-1]")
+    if key_mask is not None:
+        _req(key_mask, "key_mask", torch.uint8)
+    if out is None:
+        out = torch.empty(L, heads * 64, dtype=q.dtype, device=q.device)
+    _, ldo = _rows2d(out, "out")
+    lib = _lib.load()
+    with _Timed("t5_attention", 4.0 * L * L * heads * 64):
+        rc = lib.kr_t5_attn(q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, out.data_ptr(), ldo, L, heads,
+                            bias_delta.data_ptr(), _ptr(key_mask), _stream())
+    _lib.check(rc, "kr_t5_attn")
+    _count()
+    return out
+
+
 def ln_modulate(x: torch.Tensor, *, eps: float, weight: Optional[torch.Tensor] = None,
                 bias: Optional[torch.Tensor] = None, mod: Optional[torch.Tensor] = None,
                 shift_idx: int = 0, scale_idx: int = 1, rows_per_frame: int = 0,
@@ -278,6 +303,19 @@ def comm_scatter_rows(src: torch.Tensor, dst_peers, ld_dst: int, rows_per_peer: 
     rc = lib.kr_comm_scatter_rows(src.data_ptr(), ld, dst_peers, ld_dst, rows, src.shape[-1], rows_per_peer, world,
                                   _stream())
     _lib.check(rc, "kr_comm_scatter_rows")
+    _count()
+
+
+def kv_roll(cache: torch.Tensor, dst_row: int, src_row: int, rows: int) -> None:
+    """In-place ``cache[dst_row:dst_row+rows] = cache[src_row:src_row+rows]`` (dst_row <= src_row, overlap allowed) on a
+    [rows, width] 16-bit cache view — the eviction memmove of causal_model.py:363-373 without the clone."""
+    _req(cache, "cache")
+    n, ld = _rows2d(cache, "cache")
+    if src_row + rows > n:
+        raise _lib.KreaB200Error(f"kv_roll: rows [{src_row}, {src_row + rows}) exceed the cache ({n} rows)")
+    lib = _lib.load()
+    rc = lib.kr_kv_roll(cache.data_ptr(), ld, cache.shape[-1], dst_row, src_row, rows, _stream())
+    _lib.check(rc, "kr_kv_roll")
     _count()
 
 

@@ -99,49 +99,45 @@ class T5Encoder(nn.Module):
         self.blocks = nn.ModuleList([T5SelfAttention(dim, dim_attn, dim_ffn, num_heads, num_buckets)
                                      for _ in range(num_layers)])
         self.norm = T5LayerNorm(dim)
-        self._buckets = None            # (L, device) -> int64 [L, L]
+        self._bias_delta = None         # ((L, device, dtype), [layers][heads, 2L-1])
 
-    def _bucket_table(self, L: int, device) -> torch.Tensor:
-        if self._buckets is None or self._buckets[0] != (L, str(device)):
-            self._buckets = ((L, str(device)), relative_position_bucket(L, L, self.num_buckets, device=device))
-        return self._buckets[1]
+    def _bias_by_offset(self, L: int, device, dtype):
+        """Per layer, the relative-position bias as a function of the offset k - q (t5.py:221-264): row d of the
+        [2L-1] table is embedding[bucket(d - (L-1))].  Gathered once per (L, device, dtype) — the weights are static —
+        so the layer loop below issues kernels only."""
+        key = (L, str(device), dtype)
+        if self._bias_delta is None or self._bias_delta[0] != key:
+            b = relative_position_bucket(L, L, self.num_buckets, device=device)          # [L, L] buckets of k - q
+            by_offset = torch.cat([b[L - 1, :L - 1], b[0, :]])                              # offsets -(L-1) .. L-1
+            tabs = [blk.pos_embedding.embedding.weight.to(dtype)[by_offset].t().contiguous() for blk in self.blocks]
+            self._bias_delta = (key, tabs)
+        return self._bias_delta[1]
 
     def _encode_one(self, ids: torch.Tensor, mask: Optional[torch.Tensor]) -> torch.Tensor:
-        """ids [L], mask [L] or None -> [L, dim]."""
+        """ids [L], mask [L] or None -> [L, dim].  Per layer: rmsnorm, q/k/v GEMMs, ONE attention launch
+        (kr_t5_attn: bias + mask + fp32 softmax in the kernel), o GEMM (+residual), rmsnorm, gate GEMM (GELU),
+        fc1 GEMM (x gate in the epilogue), fc2 GEMM (+residual) — no torch arithmetic."""
         dt = self.token_embedding.weight.dtype
-        if ids.is_cuda and dt not in (torch.bfloat16, torch.float16):
-            raise TypeError(f"T5Encoder runs on 16-bit weights (the server casts it: release_server.py:141 "
+        if ids.is_cuda and dt != torch.bfloat16:
+            raise TypeError(f"T5Encoder runs on bf16 weights (the server casts it: release_server.py:141 "
                             f"text_encoder.to(dtype=torch.bfloat16)); got {dt}")
         L = ids.shape[0]
-        n, hd, da = self.num_heads, self.dim_attn // self.num_heads, self.dim_attn
+        n = self.num_heads
         x = self.token_embedding.weight[ids].contiguous()                     # [L, dim]
-        buckets = self._bucket_table(L, x.device)
-        neg = None
-        if mask is not None:                                                  # key padding: finfo.min like :107
-            neg = torch.zeros(L, dtype=dt, device=x.device).masked_fill_(mask == 0, torch.finfo(dt).min)
-        scores = torch.empty(L, L, dtype=dt, device=x.device)
-        probs = torch.empty(L, L, dtype=dt, device=x.device)
-        for blk in self.blocks:
+        tabs = self._bias_by_offset(L, x.device, dt)
+        km = None if mask is None else (mask != 0).to(torch.uint8).contiguous()
+        for blk, bias_delta in zip(self.blocks, tabs):
             at = blk.attn
             h = ops.rmsnorm(x, blk.norm1.weight, blk.norm1.eps)
             q = ops.gemm(h, at.q.weight, None)                                # [L, dim_attn]
             k = ops.gemm(h, at.k.weight, None)
-            vt = ops.gemm(at.v.weight, h, None)                               # V^T [dim_attn, L]
-            bias = blk.pos_embedding.embedding.weight[buckets].permute(2, 0, 1)      # [heads, L, L]
-            if neg is not None:
-                bias = bias + neg                                             # masked keys, every query row
-            o = torch.empty(L, da, dtype=dt, device=x.device)
-            for i in range(n):
-                cs = slice(i * hd, (i + 1) * hd)
-                ops.gemm(q[:, cs], k[:, cs], None, out=scores)                # q_h k_h^T, rounded like the einsum
-                s32 = (scores + bias[i]).float()                              # bf16 add (:110), softmax in fp32
-                ops.softmax_rows(s32, probs)
-                ops.gemm(probs, vt[cs], None, out=o[:, cs])                   # P V_h
+            v = ops.gemm(h, at.v.weight, None)
+            o = ops.t5_attention(q, k, v, bias_delta, km, heads=n)
             ops.gemm(o, at.o.weight, None, epilogue=ops.EPI_BIAS_RES, residual=x, out=x)
             h = ops.rmsnorm(x, blk.norm2.weight, blk.norm2.eps)
             g = ops.gemm(h, blk.ffn.gate[0].weight, None, epilogue=ops.EPI_BIAS_GELU)
-            f = ops.gemm(h, blk.ffn.fc1.weight, None)
-            ops.gemm(f * g, blk.ffn.fc2.weight, None, epilogue=ops.EPI_BIAS_RES, residual=x, out=x)
+            f = ops.gemm(h, blk.ffn.fc1.weight, None, epilogue=ops.EPI_MUL, residual=g)      # fc1(x) * gelu(gate(x))
+            ops.gemm(f, blk.ffn.fc2.weight, None, epilogue=ops.EPI_BIAS_RES, residual=x, out=x)
         return ops.rmsnorm(x, self.norm.weight, self.norm.eps)
 
     @torch.no_grad()

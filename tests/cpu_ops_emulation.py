@@ -14,7 +14,7 @@ import torch.nn.functional as F
 
 from oracle import dit_oracle as O
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES, EPI_BIAS_RES, EPI_F32 = 0, 1, 2, 3, 4
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES, EPI_BIAS_RES, EPI_F32, EPI_MUL = 0, 1, 2, 3, 4, 5
 launch_count = 0
 
 
@@ -37,6 +37,8 @@ def gemm(a, w, bias=None, *, epilogue=EPI_BIAS, out=None, residual=None, gate=No
         y = residual.float() + y * gate.float()[rows // rows_per_gate]
     elif epilogue == EPI_BIAS_RES:
         y = residual.float() + y
+    elif epilogue == EPI_MUL:
+        y = residual.float() * y
     elif epilogue == EPI_F32:
         return _store(out, y * alpha)
     y = y.to(a.dtype)
@@ -194,3 +196,22 @@ def vae_upsample2x(x, out):
 def softmax_rows(s, out):
     out.copy_(torch.softmax(s.float(), dim=-1).to(out.dtype))
     return out
+
+
+def kv_roll(cache, dst_row, src_row, rows):
+    cache[dst_row:dst_row + rows] = cache[src_row:src_row + rows].clone()
+
+
+def t5_attention(q, k, v, bias_delta, key_mask, *, heads, out=None):
+    """kr_t5_attn contract: no scaling, bias by offset k - q, masked keys = finfo.min, fp32 softmax."""
+    L = q.shape[0]
+    d = q.shape[-1] // heads
+    qf = q.float().reshape(L, heads, d).transpose(0, 1)
+    kf = k.float().reshape(L, heads, d).transpose(0, 1)
+    vf = v.float().reshape(L, heads, d).transpose(0, 1)
+    off = torch.arange(L)[None, :] - torch.arange(L)[:, None] + (L - 1)          # [q, k] -> table index
+    s = qf @ kf.transpose(1, 2) + bias_delta.float()[:, off]
+    if key_mask is not None:
+        s = s.masked_fill(key_mask[None, None, :] == 0, torch.finfo(torch.float32).min)
+    o = (torch.softmax(s, dim=-1) @ vf).transpose(0, 1).reshape(L, heads * d).to(q.dtype)
+    return _store(out, o)

@@ -216,3 +216,19 @@ def test_gemm_hot_shapes(N, K, epi):
         out, want = out, ref[:, :10240]
     torch.cuda.synchronize()
     assert rel_l2(out.float().cpu(), want.cpu()) < 2e-3
+
+
+@pytest.mark.parametrize("rows,evict,width,ld", [(4680, 4680, 5120, 5120), (7800, 1560, 5120, 5120), (100, 3, 256, 512),
+                                                 (17, 40, 640, 640)])
+def test_kv_roll_is_a_bit_exact_overlapping_memmove(rows, evict, width, ld):
+    """kr_kv_roll = the eviction shift of causal_model.py:363-373 (`.clone()`-based in the reference): byte-exact, also
+    when source and destination overlap (evict < rows) and when the cache view is a column slice (width < ld)."""
+    from realtime_video_b200 import ops
+    sink = 5
+    n = sink + evict + rows + 3
+    buf = torch.randn(n, ld, device="cuda").bfloat16()
+    want = buf.clone()
+    want[sink:sink + rows, :width] = buf[sink + evict:sink + evict + rows, :width]
+    ops.kv_roll(buf[:, :width], sink, sink + evict, rows)
+    torch.cuda.synchronize()
+    assert torch.equal(buf, want)

@@ -22,3 +22,67 @@ def test_t5_encoder_vs_reference_golden(tag):
     for ref in ("fp32", "bf16"):
         r = rel_l2(y.float().cpu(), g[f"{tag}/{ref}"])
         assert r < 2e-2, f"{tag} vs {ref}: rel_l2={r:.3e}"
+
+
+def _t5_attn_ref(q, k, v, bias_delta, key_mask, heads):
+    """fp32 restatement with the reference's bf16 rounding points (wan/modules/t5.py:108-112)."""
+    L, d = q.shape[0], q.shape[1] // heads
+    qf = q.float().view(L, heads, d).transpose(0, 1)
+    kf = k.float().view(L, heads, d).transpose(0, 1)
+    vf = v.float().view(L, heads, d).transpose(0, 1)
+    off = torch.arange(L, device=q.device)[None, :] - torch.arange(L, device=q.device)[:, None] + (L - 1)
+    s = (qf @ kf.transpose(1, 2)).bfloat16()
+    bias = bias_delta[:, off]                                   # [heads, L, L] bf16
+    if key_mask is not None:
+        bias = bias.masked_fill(key_mask[None, None, :] == 0, torch.finfo(torch.bfloat16).min)
+    a = torch.softmax((s + bias).float(), dim=-1).bfloat16()
+    return (a.float() @ vf).transpose(0, 1).reshape(L, heads * d)
+
+
+@pytest.mark.parametrize("L,heads,valid", [(512, 64, 512), (512, 64, 37), (200, 4, 150), (128, 2, 128), (777, 3, 700)])
+def test_t5_attention_kernel_vs_fp32_reference(L, heads, valid):
+    """kr_t5_attn (head_dim 64, bias by offset, key mask) at the UMT5-XXL shape (L 512, 64 heads) and ragged ones
+    (L not a multiple of the 128-row / 256-key tiles, 3 key tiles).  P is rounded un-normalised: rel-L2 <= 1e-2."""
+    from realtime_video_b200 import ops
+    torch.manual_seed(L + heads)
+    D = heads * 64
+    q = (torch.randn(L, D, device="cuda") * 0.6).bfloat16()
+    k = (torch.randn(L, D, device="cuda") * 0.6).bfloat16()
+    v = torch.randn(L, D, device="cuda").bfloat16()
+    bias = (torch.randn(heads, 2 * L - 1, device="cuda") * 2).bfloat16()
+    km = None
+    if valid < L:
+        km = torch.zeros(L, dtype=torch.uint8, device="cuda")
+        km[:valid] = 1
+    out = ops.t5_attention(q, k, v, bias, km, heads=heads)
+    ref = _t5_attn_ref(q, k, v, bias, km, heads)
+    r = rel_l2(out.float(), ref)
+    assert torch.isfinite(out).all() and r < 1e-2, r
+
+
+def test_umt5_xxl_dims_two_layers_vs_oracle():
+    """UMT5-XXL width (dim 4096, 64 heads x 64, ffn 10240, L 512, 32 buckets), 2 of the 24 layers, bf16 on the GPU
+    against the fp32 oracle on the host with the same seeded weights; padding rows zeroed like WanTextEncoder.
+    Tolerance: rel-L2 <= 2e-2 (the reference's own bf16-vs-fp32 gap on the fixture model is 7e-3)."""
+    from oracle.t5_oracle import T5EncoderOracle
+    from realtime_video_b200.t5 import T5Encoder
+    torch.manual_seed(0)
+    with torch.device("cuda"):
+        m = T5Encoder(vocab=1024, dim=4096, dim_attn=4096, dim_ffn=10240, num_heads=64, num_layers=2, num_buckets=32)
+    with torch.no_grad():
+        for n_, p_ in m.named_parameters():
+            if p_.dim() == 2 and "embedding" not in n_:
+                p_.normal_(std=p_.shape[1] ** -0.5)
+            elif "pos_embedding" in n_:
+                p_.normal_(std=1.0)
+            elif "norm" in n_:
+                p_.copy_(1 + 0.1 * torch.randn_like(p_))
+    m = m.to(torch.bfloat16).eval()
+    sd = {k: v.float().cpu() for k, v in m.state_dict().items()}
+    ids = torch.randint(0, 1024, (1, 512))
+    mask = torch.zeros(1, 512, dtype=torch.long)
+    mask[:, :45] = 1
+    got = m(ids.cuda(), mask.cuda())[0].float().cpu()
+    ref = T5EncoderOracle(sd, num_heads=64).forward(ids, mask)[0]
+    r = rel_l2(got[:45], ref[:45])
+    assert r < 2e-2, r
