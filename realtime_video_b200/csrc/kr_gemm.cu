@@ -271,8 +271,9 @@ static int dispatch_epi(int epi, const void* a, int lda, const void* w, int ldw,
 // KR_GEMM2: 0 = never the pair kernel, 1 = by cost (default), 2 = pair whenever N % 256 == 0 (tests)
 int gemm_plan(int epi, int M, int N, int K, bool have_workspace) {
   static const int mode = [] { const char* e = getenv("KR_GEMM2"); return e != nullptr ? atoi(e) : 1; }();
-  // KR_GEMM_SK: 0 = never stream-K, 1 = when the data-parallel wave efficiency is poor (default)
-  static const int sk_mode = [] { const char* e = getenv("KR_GEMM_SK"); return e != nullptr ? atoi(e) : 1; }();
+  // KR_GEMM_SK: 0 = never stream-K (default until it beats the data-parallel kernels: profiles/r02_gemm_ab.log),
+  // 1 = when the data-parallel wave efficiency is poor
+  static const int sk_mode = [] { const char* e = getenv("KR_GEMM_SK"); return e != nullptr ? atoi(e) : 0; }();
   if (have_workspace && sk_mode > 0 && gemm_sk_preferred(epi, M, N, K)) {
     // the CTA-pair kernel keeps shapes it fills well (its tiles are twice as large): pair waves vs stream-K
     const int sms_ = sm_count(), pairs_ = sms_ / 2;

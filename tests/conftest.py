@@ -1,5 +1,8 @@
+import os
 import sys
 from pathlib import Path
+
+os.environ.setdefault("KR_GEMM_SK", "1")      # let the stream-K GEMM tests select their kernel (plan reads it once)
 
 import pytest
 
