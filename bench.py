@@ -269,7 +269,8 @@ def _flat_roofline(prof: dict, ms_step: float, peaks: dict, traffic_db: dict) ->
                   "timed region (the timed region itself carries no per-launch events)"}
     by_kernel = {}
     for label, key in (("gemm2", "gemm/gemm2_tn_kernel"), ("gemm1", "gemm/gemm_tn_kernel"),
-                       ("gemm_streamk", "gemm/gemm_sk_kernel"), ("attn", "attention"), ("vae_conv", "vae_conv")):
+                       ("gemm_streamk", "gemm/gemm_sk_kernel"), ("gemm_flex", "gemm/gemm_flex_kernel"),
+                       ("attn", "attention"), ("vae_conv", "vae_conv")):
         a, share, n = fam(key)
         out[label + "_tflops"] = a
         out[label + "_frac"] = (a / peaks["tensor"]) if a else None

@@ -123,6 +123,7 @@ class GenerationSession:
             import torch.distributed as dist
             if first is None:
                 first = torch.empty_like(ctx[:, :1])
+            first = first.contiguous()
             dist.broadcast(first, src=0, group=sp.group)
         return torch.cat((first, ctx), dim=1)
 

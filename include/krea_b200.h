@@ -74,7 +74,8 @@ int kr_gemm_ws(int dtype, int epilogue, const void* a, int lda, const void* w, i
 size_t kr_gemm_workspace_bytes(void);
 
 /* Which kernel kr_gemm launches for this epilogue and shape: 1 = the single-CTA kernel, 2 = the CTA-pair
- * kernel (tcgen05.mma.cta_group::2, 256x256 tiles), 3 = the stream-K kernel (only with a workspace).  Host-only
+ * kernel (tcgen05.mma.cta_group::2, 256x256 tiles), 3 = the stream-K kernel (only with a workspace), 4 = the
+ * single-CTA kernel with a runtime tile width fitted to whole waves of SMs (small-M shards).  Host-only
  * queries (no launch), used by bench.py to attribute launch time per kernel. */
 int kr_gemm_kernel_id(int epilogue, int M, int N, int K);
 int kr_gemm_kernel_id_ws(int epilogue, int M, int N, int K, int have_workspace);

@@ -46,7 +46,8 @@ bool gemm_sk_preferred(int epi, int M, int N, int K);
 int gemm2_tn(int dtype, int epi, const void* a, int lda, const void* w, int ldw, const GemmParams& p,
              cudaStream_t stream);
 bool gemm_uses_pair(int epi, int M, int N, int K);
-int gemm_plan(int epi, int M, int N, int K, bool have_workspace = false);   // 0 single-CTA kernel, 1 CTA-pair kernel, 2 stream-K
+int gemm_plan(int epi, int M, int N, int K, bool have_workspace = false);   // 0 single-CTA kernel, 1 CTA-pair kernel, 2 stream-K, 3 single-CTA kernel with a wave-fitted runtime tile width
+int gemm_flex_bn(int epi, int M, int N, int K);
 
 struct AttnParams {
   void* out;           // [Lq, heads*128] 16-bit

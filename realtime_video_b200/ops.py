@@ -57,7 +57,7 @@ def profile_end() -> dict:
 
 
 # kr_gemm_kernel_id -> label used in the per-kernel timing split
-_GEMM_KERNELS = {1: "gemm_tn_kernel", 2: "gemm2_tn_kernel", 3: "gemm_sk_kernel"}
+_GEMM_KERNELS = {1: "gemm_tn_kernel", 2: "gemm2_tn_kernel", 3: "gemm_sk_kernel", 4: "gemm_flex_kernel"}
 
 # stream-K workspace (kr_gemm_ws): one zero-filled buffer per (device, stream), allocated on first use and
 # owned here (the library allocates nothing); set to False to force the data-parallel kernels
