@@ -405,6 +405,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-egress", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-secondary", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--graphs", default="auto", choices=["auto", "on", "off"],
+                    help="replay each DiT pass as a CUDA graph (auto: on for N>1 single-stream, where the host-side "
+                         "launch rate would limit the step; off on one GPU, where the device is the bottleneck)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -457,6 +460,7 @@ def main():
     models = harness.build_models(transformer, vae_decoder=vae, device=dev, vae_encoder=vae_enc)
     pe = factory.synthetic_prompt_embeds(device=dev)
     sp_mode = world > 1 and args.parallel == "sp"
+    use_graphs = args.graphs == "on" or (args.graphs == "auto" and sp_mode)
 
     def measure(sp: bool, steps: int, seed: int, profile_step: bool):
         """W warm-up blocks, then ``steps`` timed blocks (CUDA events, barrier + synchronize on both sides, max over
@@ -468,6 +472,8 @@ def main():
         else:
             transformer.model.sp = None
         decode = (not sp) or rank == 0              # one stream -> one VAE decode (rank 0)
+        transformer.use_cuda_graphs = use_graphs and sp == sp_mode
+        transformer._graphs = {}
         sess = GenerationSession(GenerateParams(num_blocks=W + steps + 1, seed=seed + (0 if sp else rank)), models,
                                  prompt_embeds=pe, device=dev, decode=decode)
         out = {"decode": decode}
@@ -597,6 +603,8 @@ def main():
                                   "(reference default keep_first_frame=False, release_server.py:571-576)",
                    "parallelism": par,
                    "l2": "weights (28 GB/pass) and KV cache exceed the 126 MB L2 every step; no flush needed",
+                   "cuda_graphs": "each DiT pass replayed as a CUDA graph (captured on its 2nd occurrence)" if use_graphs
+                                  else "off (eager launches)",
                    "dit_tflop_per_step": block_tflop},
         "egress_rgb8": egress,
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": e2e_run["h2d"],
