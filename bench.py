@@ -405,6 +405,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-egress", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-secondary", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-fp8", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--graphs", default="auto", choices=["auto", "on", "off"],
                     help="replay each DiT pass as a CUDA graph (auto: on for N>1 single-stream, where the host-side "
                          "launch rate would limit the step; off on one GPU, where the device is the bottleneck)")
@@ -560,6 +561,25 @@ def main():
                   "d2h_bytes_per_step": r["d2h"], "ms_per_step": r["ms"] / K,
                   "what": "e2e loop with kr_frames_to_rgb8 on the device and a uint8 [12,480,832,3] download"}
 
+    # FP8 tier (the reference's `enable_fp8: true`): same loop with the DiT block linears on the
+    # kind::f8f6f4 GEMM + dynamic per-tensor activation casts.  Reported beside the bf16 headline, never instead of it.
+    fp8_line = None
+    if world == 1 and not args.no_fp8:
+        from realtime_video_b200 import fp8 as fp8mod
+        fp8mod.quantize_(transformer)
+        try:
+            r8 = measure(False, max(2, K // 2), 4042, profile_step=True)
+            p8 = r8["prof"].get("gemm_fp8", {"flops": 0.0, "ms": 0.0, "n": 0})
+            fp8_line = {"value": max(2, K // 2) * FRAMES_PER_STEP / (r8["ms"] / 1e3), "unit": "frames/s",
+                        "ms_per_step": r8["ms"] / max(2, K // 2), "steps": max(2, K // 2),
+                        "gemm_fp8_tflops": p8["flops"] / (p8["ms"] * 1e-3) / 1e12 if p8["ms"] > 0 else None,
+                        "gemm_fp8_share": p8["ms"] / r8["ms_prof"] if r8["ms_prof"] > 0 else None,
+                        "what": "DiT block linears in e4m3 (per-tensor dynamic activation scale, static weight scale = "
+                                "torchao Float8DynamicActivationFloat8WeightConfig(PerTensor), release_server.py:179-182); "
+                                "attention, norms, VAE unchanged; separate numerics tier (tests/test_fp8_gpu.py)"}
+        finally:
+            fp8mod.dequantize_(transformer)
+
     # N > 1: the other way to use the box (N independent replicas, no data-path collective), same run
     secondary = None
     if world > 1 and not args.no_secondary:
@@ -617,6 +637,8 @@ def main():
     }
     if secondary is not None:
         line[secondary["mode"]] = secondary
+    if fp8_line is not None:
+        line["fp8"] = fp8_line
     emit(line)
 
 

@@ -73,6 +73,20 @@ int kr_gemm_ws(int dtype, int epilogue, const void* a, int lda, const void* w, i
                void* stream);
 size_t kr_gemm_workspace_bytes(void);
 
+/* FP8 path = what `enable_fp8: true` does to the reference's transformer (release_server.py:179-182: torchao
+ * quantize_(..., Float8DynamicActivationFloat8WeightConfig(granularity=PerTensor()))): every nn.Linear becomes
+ * a dynamic per-tensor e4m3 cast of its input followed by an FP8 matmul with fp32 accumulation and bf16 output.
+ *   kr_fp8_quantize : x [rows, cols] bf16 -> q e4m3 bytes [rows, ldq] = sat(x * 448 / amax(|x|)); state (2 floats of
+ *                     device memory) receives [amax, amax / 448]; &state[1] is the scale_a of the following GEMM.
+ *   kr_gemm_fp8     : out = epilogue((a_q @ w_q^T) * (*scale_a) * scale_w + bias), tcgen05.mma.kind::f8f6f4, bf16
+ *                     output, the epilogues of kr_gemm except KR_EPI_F32 / KR_EPI_MUL; N % 256 == 0, K % 16 == 0.
+ * Weights are quantised once by the caller (w_q = sat(w * 448 / amax(|w|)), scale_w = amax / 448). */
+int kr_fp8_quantize(const void* x, int ldx, int rows, int cols, void* q, int ldq, float* state, void* stream);
+int kr_gemm_fp8(int epilogue, const void* a, int lda, const void* w, int ldw, const float* scale_a, float scale_w,
+                const void* bias, void* out, int ldc, int M, int N, int K, const void* residual, int ldr,
+                const void* gate, int gate_stride, int rows_per_gate, void* out2, int ldc2, int n_split, int row_offset,
+                void* stream);
+
 /* Which kernel kr_gemm launches for this epilogue and shape: 1 = the single-CTA kernel, 2 = the CTA-pair
  * kernel (tcgen05.mma.cta_group::2, 256x256 tiles), 3 = the stream-K kernel (only with a workspace), 4 = the
  * single-CTA kernel with a runtime tile width fitted to whole waves of SMs (small-M shards).  Host-only

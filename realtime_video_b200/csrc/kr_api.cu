@@ -48,6 +48,24 @@ int kr_gemm_ws(int dtype, int epilogue, const void* a, int lda, const void* w, i
   return kr::gemm_tn(dtype, epilogue, a, lda, w, ldw, p, static_cast<cudaStream_t>(stream), workspace, workspace_bytes);
 }
 
+int kr_fp8_quantize(const void* x, int ldx, int rows, int cols, void* q, int ldq, float* state, void* stream) {
+  KR_REQUIRE(x && q && state, "null x/q/state");
+  return kr::fp8_quantize(x, ldx, rows, cols, q, ldq, state, static_cast<cudaStream_t>(stream));
+}
+
+int kr_gemm_fp8(int epilogue, const void* a, int lda, const void* w, int ldw, const float* scale_a, float scale_w,
+                const void* bias, void* out, int ldc, int M, int N, int K, const void* residual, int ldr,
+                const void* gate, int gate_stride, int rows_per_gate, void* out2, int ldc2, int n_split, int row_offset,
+                void* stream) {
+  KR_REQUIRE(a && w && out, "null a/w/out");
+  kr::GemmParams p;
+  p.out = out; p.bias = bias; p.residual = residual; p.gate = gate;
+  p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.ldr = ldr; p.gate_stride = gate_stride;
+  p.rows_per_gate = rows_per_gate; p.alpha = 1.0f;
+  p.out2 = out2; p.ldc2 = ldc2; p.n_split = n_split; p.row_offset = row_offset;
+  return kr::gemm_fp8_tn(epilogue, a, lda, w, ldw, p, scale_a, scale_w, static_cast<cudaStream_t>(stream));
+}
+
 int kr_attn_fwd(int dtype, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
                 void* out, int ldo, int Lq, int Lkv, int heads, float softmax_scale, int mask_mode,
                 int block_len, int window, int pad_keys, void* stream) {

@@ -28,6 +28,15 @@ import torch.nn as nn
 from . import ops
 
 
+def _linear(x: torch.Tensor, lin: nn.Linear, **kw) -> torch.Tensor:
+    """nn.Linear of a DiT block on the GEMM kernels: bf16 by default, FP8 (dynamic per-tensor activation cast +
+    kind::f8f6f4 GEMM) when ``realtime_video_b200.fp8.quantize_`` attached quantised weights to the module."""
+    q = getattr(lin, "_kr_fp8", None)
+    if q is None:
+        return ops.gemm(x, lin.weight, lin.bias, **kw)
+    return ops.linear_fp8(x, q[0], q[1], lin.bias, **kw)
+
+
 def rope_angles(max_seq_len: int, dim: int, theta: float = 10000.0) -> torch.Tensor:
     """Rotation angles pos * theta^(-2i/dim), float64 (reference rope_params, model.py:28-35)."""
     return torch.outer(torch.arange(max_seq_len, dtype=torch.float64),
@@ -271,12 +280,12 @@ class CausalWanModel(nn.Module):
             # stores every head's columns straight into the owning rank's q buffer / K slot / V slot over NVLink;
             # after the barrier this rank attends ALL rows of ITS heads and scatters the output rows back
             if sa.fused_projections:
-                qkv = ops.gemm(h, sa.to_qkv.weight, sa.to_qkv.bias)
+                qkv = _linear(h, sa.to_qkv)
                 q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
             else:
-                q = ops.gemm(h, sa.q.weight, sa.q.bias)
-                k = ops.gemm(h, sa.k.weight, sa.k.bias)
-                v = ops.gemm(h, sa.v.weight, sa.v.bias)
+                q = _linear(h, sa.q)
+                k = _linear(h, sa.k)
+                v = _linear(h, sa.v)
             q_full, o_heads, o_rows = sp.exchange_buffers(L)
             ops.qkv_norm_rope_p2p(q, k, v, sa.norm_q.weight, sa.norm_k.weight,
                                   sp.peer_ptrs(q_full[r0:]), Dh, sp.peer_ptrs(k_slot[r0:]), Dh,
@@ -303,12 +312,12 @@ class CausalWanModel(nn.Module):
             # all-to-all per tensor turns them into ALL rows of MY heads; K and V are received
             # straight into this rank's head-sharded cache slot
             if sa.fused_projections:
-                qkv = ops.gemm(h, sa.to_qkv.weight, sa.to_qkv.bias)
+                qkv = _linear(h, sa.to_qkv)
                 q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
             else:
-                q = ops.gemm(h, sa.q.weight, sa.q.bias)
-                k = ops.gemm(h, sa.k.weight, sa.k.bias)
-                v = ops.gemm(h, sa.v.weight, sa.v.bias)
+                q = _linear(h, sa.q)
+                k = _linear(h, sa.k)
+                v = _linear(h, sa.v)
             rq = torch.empty(n_loc, D, dtype=h.dtype, device=h.device)
             rk = torch.empty(n_loc, D, dtype=h.dtype, device=h.device)
             ops.qkv_norm_rope(q, k, None, sa.norm_q.weight, sa.norm_k.weight, rq, rk, None,
@@ -330,15 +339,15 @@ class CausalWanModel(nn.Module):
             return sp.heads_to_rows(o)
         if sa.fused_projections and (2 * D) % 256 == 0:
             qk = torch.empty(L, 2 * D, dtype=h.dtype, device=h.device)
-            ops.gemm(h, sa.to_qkv.weight, sa.to_qkv.bias, out=qk, out2=v_slot, n_split=2 * D)
+            _linear(h, sa.to_qkv, out=qk, out2=v_slot, n_split=2 * D)
             q, k, v = qk[:, :D], qk[:, D:], None
         elif sa.fused_projections:
-            qkv = ops.gemm(h, sa.to_qkv.weight, sa.to_qkv.bias)
+            qkv = _linear(h, sa.to_qkv)
             q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
         else:
-            q = ops.gemm(h, sa.q.weight, sa.q.bias)
-            k = ops.gemm(h, sa.k.weight, sa.k.bias)
-            ops.gemm(h, sa.v.weight, sa.v.bias, out=v_slot)
+            q = _linear(h, sa.q)
+            k = _linear(h, sa.k)
+            _linear(h, sa.v, out=v_slot)
             v = None
         rq = torch.empty(L, D, dtype=h.dtype, device=h.device)
         ops.qkv_norm_rope(q, k, v, sa.norm_q.weight, sa.norm_k.weight, rq, k_slot,
@@ -358,14 +367,14 @@ class CausalWanModel(nn.Module):
         """wan/modules/model.py:171-228 (K/V of the prompt computed once, cached by assignment)."""
         ca = blk.cross_attn
         D = self.dim
-        q = ops.gemm(h, ca.q.weight, ca.q.bias)
+        q = _linear(h, ca.q)
         ops.rmsnorm(q, ca.norm_q.weight, ca.eps, out=q)
         if cache is not None and cache["is_init"]:
             k, v = cache["k"], cache["v"]
         else:
-            k = ops.gemm(ctx, ca.k.weight, ca.k.bias)
+            k = _linear(ctx, ca.k)
             ops.rmsnorm(k, ca.norm_k.weight, ca.eps, out=k)
-            v = ops.gemm(ctx, ca.v.weight, ca.v.bias)
+            v = _linear(ctx, ca.v)
             k = k.view(1, -1, ca.num_heads, ca.head_dim)
             v = v.view(1, -1, ca.num_heads, ca.head_dim)
             if cache is not None:
@@ -383,7 +392,7 @@ class CausalWanModel(nn.Module):
                             row_offset=r0)
         y = self._self_attention(blk, h, grid, kv_cache, current_start, mask)
         sa = blk.self_attn
-        ops.gemm(y, sa.o.weight, sa.o.bias, epilogue=ops.EPI_BIAS_GATE_RES, residual=x,
+        _linear(y, sa.o, epilogue=ops.EPI_BIAS_GATE_RES, residual=x,
                  gate=emod[:, 2], rows_per_gate=fs, out=x, row_offset=r0)
         n3 = blk.norm3
         if isinstance(n3, nn.LayerNorm):
@@ -392,11 +401,11 @@ class CausalWanModel(nn.Module):
             h = x
         y = self._cross_attention(blk, h, ctx, crossattn_cache)
         ca = blk.cross_attn
-        ops.gemm(y, ca.o.weight, ca.o.bias, epilogue=ops.EPI_BIAS_RES, residual=x, out=x)
+        _linear(y, ca.o, epilogue=ops.EPI_BIAS_RES, residual=x, out=x)
         h = ops.ln_modulate(x, eps=blk.eps, mod=emod, shift_idx=3, scale_idx=4, rows_per_frame=fs, out=h,
                             row_offset=r0)
-        hid = ops.gemm(h, blk.ffn[0].weight, blk.ffn[0].bias, epilogue=ops.EPI_BIAS_GELU)
-        ops.gemm(hid, blk.ffn[2].weight, blk.ffn[2].bias, epilogue=ops.EPI_BIAS_GATE_RES, residual=x,
+        hid = _linear(h, blk.ffn[0], epilogue=ops.EPI_BIAS_GELU)
+        _linear(hid, blk.ffn[2], epilogue=ops.EPI_BIAS_GATE_RES, residual=x,
                  gate=emod[:, 5], rows_per_gate=fs, out=x, row_offset=r0)
         return x
 

@@ -12,6 +12,8 @@ resolving to the reference checkout, independent of the ``sys.path`` order:
     demo_utils.vae_block3      -> realtime_video_b200.vae           (VAEDecoderWrapper, VAEEncoderWrapper; vae_block3.py:116-230)
     demo_utils.vae             -> realtime_video_b200.vae           (VAEDecoderWrapperSingle, ZERO_VAE_CACHE, ...; demo_utils/vae.py:150-195)
     wan.modules.causal_model   -> realtime_video_b200.dit           (CausalWanModel; wan/modules/causal_model.py:526)
+    torchao.quantization.quant_api -> realtime_video_b200.fp8       (quantize_, Float8DynamicActivationFloat8WeightConfig,
+                                                                     PerTensor: the `enable_fp8` lines release_server.py:179-182)
 
 The served module IS the product module (same object under both names), so ``isinstance`` checks and class
 identity hold across the two spellings.  The reference's ``CausalInferencePipeline`` and ``GenerationSession``
@@ -36,6 +38,8 @@ ALIASES = {
     "demo_utils.vae_block3": "realtime_video_b200.vae",
     "demo_utils.vae": "realtime_video_b200.vae",
     "wan.modules.causal_model": "realtime_video_b200.dit",
+    # `enable_fp8: true` (release_server.py:179-182): quantize_ / Float8DynamicActivationFloat8WeightConfig / PerTensor
+    "torchao.quantization.quant_api": "realtime_video_b200.fp8",
 }
 
 

@@ -176,6 +176,64 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     return out
 
 
+_fp8_scratch = {}
+
+
+def fp8_quantize(x: torch.Tensor, q: Optional[torch.Tensor] = None, state: Optional[torch.Tensor] = None):
+    """Dynamic per-tensor e4m3 cast (torchao Float8DynamicActivation, PerTensor): x [rows, cols] bf16 ->
+    (q uint8 bytes [rows, cols], state float32 [2] = [amax, dequantisation scale amax / 448])."""
+    _req(x, "x", torch.bfloat16)
+    rows, ld = _rows2d(x, "x")
+    cols = x.shape[-1]
+    if q is None:
+        q = torch.empty(rows, cols, dtype=torch.uint8, device=x.device)
+    if state is None:
+        state = torch.empty(2, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    rc = lib.kr_fp8_quantize(x.data_ptr(), ld, rows, cols, q.data_ptr(), q.stride(0), state.data_ptr(), _stream())
+    _lib.check(rc, "kr_fp8_quantize")
+    _count(2)
+    return q, state
+
+
+def gemm_fp8(a_q: torch.Tensor, w_q: torch.Tensor, scale_a: torch.Tensor, scale_w: float,
+             bias: Optional[torch.Tensor] = None, *, epilogue: int = EPI_BIAS, out: Optional[torch.Tensor] = None,
+             residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None, rows_per_gate: int = 0,
+             out2: Optional[torch.Tensor] = None, n_split: int = 0, row_offset: int = 0) -> torch.Tensor:
+    """out[M,N] (bf16) = epilogue((a_q[M,K] @ w_q[N,K]^T) * scale_a[1] * scale_w + bias); a_q / w_q e4m3 bytes,
+    scale_a the ``state`` tensor of :func:`fp8_quantize`."""
+    _req(a_q, "a_q", torch.uint8); _req(w_q, "w_q", torch.uint8)
+    M, K = a_q.shape
+    N = w_q.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=a_q.device)
+    _, ldc = _rows2d(out, "out")
+    ldr = _rows2d(residual, "residual")[1] if residual is not None else 0
+    gs = gate.stride(0) if gate is not None and gate.dim() >= 2 else 0
+    ldc2 = _rows2d(out2, "out2")[1] if out2 is not None else 0
+    lib = _lib.load()
+    with _Timed("gemm_fp8", 2.0 * M * N * K):
+        rc = lib.kr_gemm_fp8(epilogue, a_q.data_ptr(), a_q.stride(0), w_q.data_ptr(), w_q.stride(0),
+                             scale_a.data_ptr() + 4, scale_w, _ptr(bias), out.data_ptr(), ldc, M, N, K, _ptr(residual),
+                             ldr, _ptr(gate), gs, rows_per_gate, _ptr(out2), ldc2, n_split, row_offset, _stream())
+    _lib.check(rc, "kr_gemm_fp8")
+    _count()
+    return out
+
+
+def linear_fp8(x: torch.Tensor, w_q: torch.Tensor, scale_w: float, bias: Optional[torch.Tensor] = None, **kw):
+    """Float8 dynamic-activation linear: quantise ``x`` per tensor, then the FP8 GEMM (scratch buffers are reused per
+    (device, shape); the launches are stream-ordered)."""
+    rows, _ = _rows2d(x, "x")
+    key = (x.device.index, rows, x.shape[-1])
+    sc = _fp8_scratch.get(key)
+    if sc is None:
+        sc = _fp8_scratch[key] = (torch.empty(rows, x.shape[-1], dtype=torch.uint8, device=x.device),
+                                  torch.empty(2, dtype=torch.float32, device=x.device))
+    q, state = fp8_quantize(x if x.dim() == 2 else x.reshape(rows, -1), sc[0], sc[1])
+    return gemm_fp8(q, w_q, state, scale_w, bias, **kw)
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, heads: int,
               out: Optional[torch.Tensor] = None, softmax_scale: Optional[float] = None,
               block_len: int = 0, window: int = 0, pad_keys: int = 0) -> torch.Tensor:

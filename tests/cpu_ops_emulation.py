@@ -215,3 +215,11 @@ def t5_attention(q, k, v, bias_delta, key_mask, *, heads, out=None):
         s = s.masked_fill(key_mask[None, None, :] == 0, torch.finfo(torch.float32).min)
     o = (torch.softmax(s, dim=-1) @ vf).transpose(0, 1).reshape(L, heads * d).to(q.dtype)
     return _store(out, o)
+
+
+def linear_fp8(x, w_q, scale_w, bias=None, **kw):
+    """kr_fp8_quantize + kr_gemm_fp8 contract (w_q: e4m3 bytes as uint8)."""
+    amax = x.abs().max().float().clamp(min=1e-12)
+    xq = (x.float() * (448.0 / amax)).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).float()
+    a = (xq * (amax / 448.0) * scale_w).to(torch.float32)              # fold the dequantisation into the operand
+    return gemm(a, w_q.view(torch.float8_e4m3fn).float(), bias, **kw)
