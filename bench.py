@@ -406,9 +406,10 @@ def main():
     ap.add_argument("--no-egress", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-secondary", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-fp8", action="store_true", help=argparse.SUPPRESS)
-    ap.add_argument("--graphs", default="auto", choices=["auto", "on", "off"],
-                    help="replay each DiT pass as a CUDA graph (auto: on for N>1 single-stream, where the host-side "
-                         "launch rate would limit the step; off on one GPU, where the device is the bottleneck)")
+    ap.add_argument("--graphs", default="off", choices=["on", "off"],
+                    help="replay each DiT pass as a CUDA graph (validated on one GPU, tests/test_server_loop_gpu.py; "
+                         "NOT with the multi-GPU exchange inside the capture: an 8-GPU run with it on hung)")
+    ap.add_argument("--watchdog-s", type=int, default=420, help=argparse.SUPPRESS)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -422,6 +423,16 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if world > 1 and args.watchdog_s > 0:
+        # a multi-rank run that stops making progress (a rank died, a peer never arrived at a barrier) must not sit
+        # on N GPUs until an outer limit fires: hard exit after watchdog_s
+        def _bail():
+            sys.stderr.write(f"bench.py: watchdog fired after {args.watchdog_s} s on rank {rank}; exiting\n")
+            sys.stderr.flush()
+            os._exit(3)
+        _wd = threading.Timer(args.watchdog_s, _bail)
+        _wd.daemon = True
+        _wd.start()
     if world > 1:
         import torch.distributed as dist
         # stdout carries exactly ONE JSON line: keep NCCL's "NCCL version ..." banner off it
@@ -461,7 +472,7 @@ def main():
     models = harness.build_models(transformer, vae_decoder=vae, device=dev, vae_encoder=vae_enc)
     pe = factory.synthetic_prompt_embeds(device=dev)
     sp_mode = world > 1 and args.parallel == "sp"
-    use_graphs = args.graphs == "on" or (args.graphs == "auto" and sp_mode)
+    use_graphs = args.graphs == "on"
 
     def measure(sp: bool, steps: int, seed: int, profile_step: bool):
         """W warm-up blocks, then ``steps`` timed blocks (CUDA events, barrier + synchronize on both sides, max over

@@ -43,5 +43,28 @@ elif which == "conv":
         for _ in range(3):
             ops.vae_conv(x, c.weight, c.bias, n=c.n, cout=c.cout, T=T, taps=(3, 3, 3), tile=_tile_for(Hh, Ww),
                          out_raw=out, out_norm=nrm, gamma=gamma, residual=out)
+elif which == "flex":    # o-projection on a sequence-parallel shard (M = 585): wave-fitted runtime tile width
+    a = torch.randn(585, D, device=dev, dtype=torch.bfloat16)
+    w = torch.randn(D, D, device=dev, dtype=torch.bfloat16) * 0.02
+    b = torch.zeros(D, device=dev, dtype=torch.bfloat16)
+    o = torch.empty(585, D, device=dev, dtype=torch.bfloat16)
+    for _ in range(4):
+        ops.gemm(a, w, b, out=o)
+elif which == "fp8":     # ffn.0 in e4m3
+    from realtime_video_b200 import fp8
+    a = torch.randn(L, D, device=dev, dtype=torch.bfloat16)
+    w = torch.randn(FF, D, device=dev, dtype=torch.bfloat16) * 0.02
+    wq, sw = fp8.quantize_weight(w)
+    b = torch.zeros(FF, device=dev, dtype=torch.bfloat16)
+    o = torch.empty(L, FF, device=dev, dtype=torch.bfloat16)
+    for _ in range(4):
+        ops.linear_fp8(a, wq, sw, b, epilogue=ops.EPI_BIAS_GELU, out=o)
+elif which == "t5attn":
+    q = torch.randn(512, 4096, device=dev, dtype=torch.bfloat16)
+    k = torch.randn(512, 4096, device=dev, dtype=torch.bfloat16)
+    v = torch.randn(512, 4096, device=dev, dtype=torch.bfloat16)
+    bias = torch.randn(64, 1023, device=dev, dtype=torch.bfloat16)
+    for _ in range(4):
+        ops.t5_attention(q, k, v, bias, None, heads=64)
 torch.cuda.synchronize()
 print("done", which)
