@@ -62,8 +62,9 @@ def test_t5_attention_kernel_vs_fp32_reference(L, heads, valid):
 
 def test_umt5_xxl_dims_two_layers_vs_oracle():
     """UMT5-XXL width (dim 4096, 64 heads x 64, ffn 10240, L 512, 32 buckets), 2 of the 24 layers, bf16 on the GPU
-    against the fp32 oracle on the host with the same seeded weights; padding rows zeroed like WanTextEncoder.
-    Tolerance: rel-L2 <= 2e-2 (the reference's own bf16-vs-fp32 gap on the fixture model is 7e-3)."""
+    against the fp32 oracle on the host with the same seeded weights.  Yardstick measured in the same test: the gap of
+    the ORACLE run in bf16 (the reference's own execution dtype, torch CPU kernels) to its fp32 run on these weights;
+    the CUDA path must stay within 1.5x that gap + 5e-3 (and under 5e-2 absolutely)."""
     from oracle.t5_oracle import T5EncoderOracle
     from realtime_video_b200.t5 import T5Encoder
     torch.manual_seed(0)
@@ -84,5 +85,6 @@ def test_umt5_xxl_dims_two_layers_vs_oracle():
     mask[:, :45] = 1
     got = m(ids.cuda(), mask.cuda())[0].float().cpu()
     ref = T5EncoderOracle(sd, num_heads=64).forward(ids, mask)[0]
-    r = rel_l2(got[:45], ref[:45])
-    assert r < 2e-2, r
+    ref16 = T5EncoderOracle({k: v.bfloat16() for k, v in sd.items()}, num_heads=64).forward(ids, mask)[0].float()
+    r, r16 = rel_l2(got[:45], ref[:45]), rel_l2(ref16[:45], ref[:45])
+    assert r < 1.5 * r16 + 5e-3 and r < 5e-2, (r, r16)

@@ -25,7 +25,7 @@ def timeit(fn, n=20, warm=5):
 
 
 lib = _lib.load()
-names = {1: "single", 2: "pair", 3: "streamK"}
+names = {1: "single", 2: "pair", 3: "streamK", 4: "flex"}
 print("shape                      | ours(ws) kernel TF/s | ours(no ws) kernel TF/s | cuBLAS TF/s | ours/cuBLAS")
 for M in (4680, 2340, 1170, 585):
     for (N, K, name) in [(15360, 5120, "qkv"), (5120, 5120, "proj"), (13824, 5120, "ffn1"), (5120, 13824, "ffn2")]:
