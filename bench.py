@@ -409,7 +409,7 @@ def main():
     ap.add_argument("--graphs", default="off", choices=["on", "off"],
                     help="replay each DiT pass as a CUDA graph (validated on one GPU, tests/test_server_loop_gpu.py; "
                          "NOT with the multi-GPU exchange inside the capture: an 8-GPU run with it on hung)")
-    ap.add_argument("--watchdog-s", type=int, default=420, help=argparse.SUPPRESS)
+    ap.add_argument("--watchdog-s", type=int, default=600, help=argparse.SUPPRESS)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

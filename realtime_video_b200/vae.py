@@ -304,8 +304,9 @@ class DecoderEngine:
         H, W = x.shape[1], x.shape[2]
         ops.vae_conv(x, c.weight, c.bias, n=c.n, cout=c.cout, T=T, taps=c.taps, tile=_tile_for(H, W), **kw)
         if src is None and c.taps[0] == 3:
-            tail = c.buf[T:T + 2]                  # roll: last two input frames become the cache
-            c.buf[:2].copy_(tail.clone() if T < 2 else tail)
+            # roll: the last two input frames become the cache (frames = rows of a [frames, H*W*C] view; the
+            # in-place row shift is overlap-safe, so T = 1 needs no temporary)
+            ops.kv_roll(c.buf.view(c.buf.shape[0], -1), 0, T, 2)
 
     def _new(self, t, h, w, c):
         return torch.empty(t, h, w, c, dtype=self.dtype, device=self.device)
@@ -691,8 +692,7 @@ class EncoderEngine:
         ops.vae_conv(x, c.weight, c.bias, n=c.n, cout=c.cout, T=T, taps=c.taps,
                      tile=_tile_for(x.shape[1], x.shape[2]), **kw)
         if src is None and c.taps[0] == 3:
-            tail = c.buf[T:T + 2]                  # roll: the last two input frames become the cache
-            c.buf[:2].copy_(tail.clone() if T < 2 else tail)
+            ops.kv_roll(c.buf.view(c.buf.shape[0], -1), 0, T, 2)     # roll the feature cache (see DecoderEngine._conv)
 
     # -- one chunk ---------------------------------------------------------------------------------
     def encode_chunk(self, frames: torch.Tensor, first: bool) -> torch.Tensor:
