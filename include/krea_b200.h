@@ -217,6 +217,26 @@ int kr_softmax_rows(int dtype, const float* s, long ld, void* p, long ldo, int r
  * 12-frame 832x480 block.  `pixels` must be contiguous. */
 int kr_frames_to_rgb8(const float* pixels, unsigned char* rgb, int frames, int height, int width, void* stream);
 
+/* Frame egress, second half: the JPEG files the reference produces on the host for every frame,
+ * `TF.to_pil_image(frames[0, idx], "RGB").save(io, format='JPEG', quality=90)` (release_server.py:973; Pillow ->
+ * libjpeg-turbo in a 24-thread pool), encoded on the device and BYTE-IDENTICAL to Pillow's output: integer
+ * RGB->YCbCr, 4:2:0 box downsampling, "islow" DCT, round-half-away quantisation with the Annex K tables scaled by
+ * `quality`, baseline Huffman coding, 0xFF stuffing, libjpeg's marker layout.  Per 12-frame 832x480 block ~1-3 MB
+ * leave the device instead of 57.5 MB (fp32) or 14.4 MB (RGB8).
+ *   kr_frames_to_jpeg : pixels fp32 [frames, 3, H, W] in [-1, 1], contiguous, 16-byte aligned (the decoder's
+ *                       output; normalised exactly like kr_frames_to_rgb8)
+ *   kr_rgb8_to_jpeg   : rgb bytes [frames, H, W, 3], contiguous, 8-byte aligned
+ * H and W must be multiples of 16 (true for every resolution of the path: pixels = 8 x latent, latent dims even).
+ * out: [frames, cap] bytes (cap % 4 == 0, out 4-byte aligned); file f starts at out + f * cap and has sizes[f]
+ * bytes; sizes[f] < 0 means the file needs -sizes[f] bytes and did not fit (nothing is written past cap).
+ * workspace: kr_jpeg_workspace_bytes(frames, H, W) bytes of device memory, 256-byte aligned, private to the stream
+ * for the duration of the call (coefficients, bit offsets, the unstuffed bit stream).  Four launches, no host sync. */
+size_t kr_jpeg_workspace_bytes(int frames, int height, int width);
+int kr_frames_to_jpeg(const float* pixels, int frames, int height, int width, int quality, unsigned char* out,
+                      long cap, int* sizes, void* workspace, size_t workspace_bytes, void* stream);
+int kr_rgb8_to_jpeg(const unsigned char* rgb, int frames, int height, int width, int quality, unsigned char* out,
+                    long cap, int* sizes, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,7 @@ from pathlib import Path
 _PKG_DIR = Path(__file__).resolve().parent
 _CSRC = _PKG_DIR / "csrc"
 LIB_PATH = _PKG_DIR / "libkrea_b200.so"
-SOURCES = ["kr_host.cu", "kr_gemm.cu", "kr_gemm2.cu", "kr_gemm_sk.cu", "kr_gemm_fp8.cu", "kr_attn.cu", "kr_t5attn.cu", "kr_dit_elem.cu", "kr_vae.cu", "kr_api.cu"]
+SOURCES = ["kr_host.cu", "kr_gemm.cu", "kr_gemm2.cu", "kr_gemm_sk.cu", "kr_gemm_fp8.cu", "kr_attn.cu", "kr_t5attn.cu", "kr_dit_elem.cu", "kr_vae.cu", "kr_jpeg.cu", "kr_api.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -120,6 +120,8 @@ SIGNATURES = {
     "kr_vae_scale_input": [_i, _vp, _l, _l, _l, _l, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "kr_softmax_rows": [_i, _vp, _l, _vp, _l, _i, _i, _vp],
     "kr_frames_to_rgb8": [_vp, _vp, _i, _i, _i, _vp],
+    "kr_frames_to_jpeg": [_vp, _i, _i, _i, _i, _vp, _l, _vp, _vp, _sz, _vp],
+    "kr_rgb8_to_jpeg": [_vp, _i, _i, _i, _i, _vp, _l, _vp, _vp, _sz, _vp],
 }
 
 
@@ -142,6 +144,9 @@ def load() -> ctypes.CDLL:
         lib.kr_last_error.argtypes = []
         lib.kr_gemm_workspace_bytes.restype = _sz
         lib.kr_gemm_workspace_bytes.argtypes = []
+        if hasattr(lib, "kr_jpeg_workspace_bytes"):
+            lib.kr_jpeg_workspace_bytes.restype = _sz
+            lib.kr_jpeg_workspace_bytes.argtypes = [_i, _i, _i]
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name, None)
             if fn is None:

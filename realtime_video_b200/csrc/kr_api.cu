@@ -240,4 +240,22 @@ int kr_frames_to_rgb8(const float* pixels, uint8_t* rgb, int frames, int height,
   return kr::frames_to_rgb8(pixels, rgb, frames, height, width, static_cast<cudaStream_t>(stream));
 }
 
+size_t kr_jpeg_workspace_bytes(int frames, int height, int width) {
+  return kr::jpeg_workspace_bytes(frames, height, width);
+}
+
+int kr_frames_to_jpeg(const float* pixels, int frames, int height, int width, int quality, unsigned char* out,
+                      long cap, int* sizes, void* workspace, size_t workspace_bytes, void* stream) {
+  KR_REQUIRE(pixels && out && sizes, "null pointer");
+  return kr::frames_to_jpeg(pixels, 0, frames, height, width, quality, out, cap, sizes, workspace, workspace_bytes,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int kr_rgb8_to_jpeg(const unsigned char* rgb, int frames, int height, int width, int quality, unsigned char* out,
+                    long cap, int* sizes, void* workspace, size_t workspace_bytes, void* stream) {
+  KR_REQUIRE(rgb && out && sizes, "null pointer");
+  return kr::frames_to_jpeg(rgb, 1, frames, height, width, quality, out, cap, sizes, workspace, workspace_bytes,
+                            static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

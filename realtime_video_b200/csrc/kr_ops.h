@@ -146,4 +146,10 @@ int vae_scale_input(int dtype, const void* z, long zt, long zc, long zh, long zw
 int softmax_rows(int dtype, const float* s, long ld, void* pout, long ldo, int rows, int cols,
                  cudaStream_t stream);
 int frames_to_rgb8(const float* pixels, uint8_t* rgb, int frames, int height, int width, cudaStream_t stream);
+// device-side baseline JPEG (kr_jpeg.cu): byte-identical to Pillow's save(format='JPEG', quality=q) of each frame.
+// src_kind 0: fp32 planar [frames, 3, H, W] in [-1, 1] (normalised like frames_to_rgb8); 1: RGB bytes [frames, H, W, 3].
+// out [frames, cap] bytes, sizes[frames] = bytes of each file (negative: -(bytes needed), the file did not fit in cap).
+size_t jpeg_workspace_bytes(int frames, int height, int width);
+int frames_to_jpeg(const void* src, int src_kind, int frames, int height, int width, int quality, uint8_t* out,
+                   long cap, int* sizes, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 }  // namespace kr

@@ -566,3 +566,70 @@ def frames_to_rgb8(pixels: torch.Tensor, out: Optional[torch.Tensor] = None) -> 
     _lib.check(rc, "kr_frames_to_rgb8")
     _count()
     return out
+
+
+_jpeg_ws = {}
+
+
+def frames_to_jpeg(pixels: torch.Tensor, quality: int = 90, *, cap: Optional[int] = None,
+                   out: Optional[torch.Tensor] = None, sizes: Optional[torch.Tensor] = None):
+    """Decoder output fp32 [..., T, 3, H, W] in [-1, 1] (or RGB bytes uint8 [..., T, H, W, 3]) -> one baseline JPEG
+    file per frame, byte-identical to the reference's host-side
+    ``TF.to_pil_image(frames[0, idx], "RGB").save(io, format='JPEG', quality=90)`` (release_server.py:973), encoded
+    on the device.  Returns ``(out uint8 [T, cap], sizes int32 [T])``: file f is ``out[f, :sizes[f]]``; a negative
+    size means the file needs ``-sizes[f]`` bytes and did not fit into ``cap`` (default: the raw RGB size).
+    The workspace (coefficients, bit offsets, bit stream) is cached per (device, stream, shape)."""
+    if pixels.dtype == torch.float32:
+        _req(pixels, "pixels", torch.float32)
+        if pixels.dim() < 4 or pixels.shape[-3] != 3 or not pixels.is_contiguous():
+            raise _lib.KreaB200Error("frames_to_jpeg: expected contiguous fp32 [..., T, 3, H, W]")
+        lead, (H, W) = pixels.shape[:-3], pixels.shape[-2:]
+        fn = "kr_frames_to_jpeg"
+    else:
+        _req(pixels, "pixels", torch.uint8)
+        if pixels.dim() < 4 or pixels.shape[-1] != 3 or not pixels.is_contiguous():
+            raise _lib.KreaB200Error("frames_to_jpeg: expected contiguous uint8 [..., T, H, W, 3]")
+        lead, (H, W) = pixels.shape[:-3], pixels.shape[-3:-1]
+        fn = "kr_rgb8_to_jpeg"
+    T = 1
+    for d in lead:
+        T *= int(d)
+    H, W = int(H), int(W)
+    lib = _lib.load()
+    need = lib.kr_jpeg_workspace_bytes(T, H, W)
+    if need == 0:
+        raise _lib.KreaB200Error(f"frames_to_jpeg: {T} frames of {H}x{W} unsupported (H and W must be multiples of 16)")
+    if cap is None:
+        cap = (H * W * 3 + 4096 + 3) // 4 * 4
+    if out is None:
+        out = torch.empty(T, cap, dtype=torch.uint8, device=pixels.device)
+    elif out.dtype != torch.uint8 or not out.is_contiguous() or tuple(out.shape) != (T, cap):
+        raise _lib.KreaB200Error("frames_to_jpeg: out must be contiguous uint8 [T, cap]")
+    if sizes is None:
+        sizes = torch.empty(T, dtype=torch.int32, device=pixels.device)
+    elif sizes.dtype != torch.int32 or not sizes.is_contiguous() or sizes.numel() != T:
+        raise _lib.KreaB200Error("frames_to_jpeg: sizes must be contiguous int32 [T]")
+    _req(out, "out"); _req(sizes, "sizes")
+    stream = _stream()
+    key = (pixels.device.index, stream, T, H, W)
+    ws = _jpeg_ws.get(key)
+    if ws is None:
+        if len(_jpeg_ws) > 8:
+            _jpeg_ws.clear()
+        ws = _jpeg_ws[key] = torch.empty(need, dtype=torch.uint8, device=pixels.device)
+    rc = getattr(lib, fn)(pixels.data_ptr(), T, H, W, int(quality), out.data_ptr(), cap, sizes.data_ptr(),
+                          ws.data_ptr(), ws.numel(), stream)
+    _lib.check(rc, fn)
+    _count(4)
+    return out, sizes
+
+
+def jpeg_files(out: torch.Tensor, sizes: torch.Tensor) -> list:
+    """Host-side convenience: the JPEG files of :func:`frames_to_jpeg` as ``bytes`` objects (one small device->host
+    read of the sizes, then only the used prefix of every file crosses PCIe)."""
+    n = sizes.cpu()
+    if int(n.min()) <= 0:
+        raise _lib.KreaB200Error(f"frames_to_jpeg: a file did not fit its buffer (sizes {n.tolist()})")
+    m = int(n.max())
+    host = out[:, :m].cpu()
+    return [host[i, :int(n[i])].numpy().tobytes() for i in range(host.shape[0])]
