@@ -92,3 +92,38 @@ def test_capacity_overflow_is_reported_and_nothing_is_written_past_cap(emu):
     assert big[cap:cap + sizes[1]].tobytes() == pillow_jpeg(frames[1], 90)     # frame 1 intact, right after cap
     assert (big[T * cap:] == 0xEE).all()
     assert big[:cap].tobytes() == pillow_jpeg(img, 90)[:cap]                   # the truncated prefix is still right
+
+
+def test_python_op_argument_plumbing_with_the_emulator_behind_the_abi(emu, monkeypatch):
+    """ops.frames_to_jpeg / ops.jpeg_files on CPU tensors with the C ABI replaced by the host emulator: checks the
+    wrapper's shape handling, default capacity, argument order and the host-side file extraction."""
+    import torch
+    from realtime_video_b200 import _lib, ops
+
+    real = _lib.load()
+
+    class FakeLib:
+        def kr_jpeg_workspace_bytes(self, T, H, W):
+            return real.kr_jpeg_workspace_bytes(T, H, W)               # host-only size query of the real library
+
+        def _run(self, kind, src, T, H, W, q, out, cap, sizes, ws, ws_bytes, stream):
+            assert ws_bytes >= self.kr_jpeg_workspace_bytes(T, H, W) > 0
+            return emu.jpeg_emulate(src, kind, T, H, W, q, out, cap, sizes, 1024, None)
+
+        def kr_frames_to_jpeg(self, *a):
+            return self._run(0, *a)
+
+        def kr_rgb8_to_jpeg(self, *a):
+            return self._run(1, *a)
+
+    monkeypatch.setattr(ops._lib, "load", lambda: FakeLib())
+    monkeypatch.setattr(ops._lib, "check", lambda rc, what: None if rc == 0 else (_ for _ in ()).throw(AssertionError(rc)))
+    monkeypatch.setattr(ops, "_req", lambda t, name, dtype=None: None)
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    x = frames_fp32(4, 32, 48, seed=9)
+    out, sizes = ops.frames_to_jpeg(torch.from_numpy(x)[None], 90)            # [1, T, 3, H, W] like the server's tensor
+    assert tuple(out.shape) == (4, (32 * 48 * 3 + 4096 + 3) // 4 * 4) and sizes.dtype == torch.int32
+    assert ops.jpeg_files(out, sizes) == jpeg_oracle.frames_to_jpeg(x, 90)
+    img = images(32, 48)["smooth"]
+    out, sizes = ops.frames_to_jpeg(torch.from_numpy(img)[None], 75)
+    assert ops.jpeg_files(out, sizes) == [pillow_jpeg(img, 75)]
