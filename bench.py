@@ -519,7 +519,7 @@ def main():
                 out["prof"], out["ms_prof"] = ops.profile_end(), p0.elapsed_time(p1)
         return out
 
-    def measure_e2e(sp: bool, steps: int, seed: int, rgb8: bool = False):
+    def measure_e2e(sp: bool, steps: int, seed: int, rgb8: bool = False, jpeg: bool = False):
         """Same loop through the same public API with HOST buffers: the block's noise from pinned host memory every
         step and the decoded frames back to pinned host memory inside the timed region."""
         decode = (not sp) or rank == 0
@@ -527,7 +527,14 @@ def main():
                                  prompt_embeds=pe, device=dev, decode=decode)
         nf = 3
         host_noise = sess.noise.cpu().pin_memory()
-        if rgb8:
+        jpeg_bytes = 0
+        if jpeg:
+            jcap = 480 * 832 * 3
+            host_out = torch.empty(12, jcap, dtype=torch.uint8).pin_memory()
+            host_sizes = torch.empty(12, dtype=torch.int32).pin_memory()
+            dev_jpg = torch.empty(12, jcap, dtype=torch.uint8, device=dev)
+            dev_sizes = torch.empty(12, dtype=torch.int32, device=dev)
+        elif rgb8:
             host_out = torch.empty(1, 12, 480, 832, 3, dtype=torch.uint8).pin_memory()
             dev_rgb = torch.empty(1, 12, 480, 832, 3, dtype=torch.uint8, device=dev)
         else:
@@ -543,7 +550,17 @@ def main():
                 sess.noise[:, s0:s0 + nf].copy_(host_noise[:, s0:s0 + nf], non_blocking=True)      # H2D
                 px = sess.generate_block()
                 if decode:
-                    if rgb8:
+                    if jpeg:
+                        # the reference's per-frame JPEG (release_server.py:973) encoded on the device: first the 12
+                        # file sizes, then only the used bytes of every file cross PCIe
+                        ops.frames_to_jpeg(px, 90, cap=jcap, out=dev_jpg, sizes=dev_sizes)
+                        host_sizes.copy_(dev_sizes, non_blocking=True)
+                        torch.cuda.current_stream().synchronize()
+                        for f, nb in enumerate(host_sizes.tolist()):
+                            assert nb > 0, "JPEG file did not fit its buffer"
+                            host_out[f, :nb].copy_(dev_jpg[f, :nb], non_blocking=True)
+                            jpeg_bytes += nb
+                    elif rgb8:
                         ops.frames_to_rgb8(px, out=dev_rgb)
                         host_out.copy_(dev_rgb, non_blocking=True)
                     else:
@@ -553,7 +570,7 @@ def main():
             barrier()
         return {"ms": max_over_ranks(t0.elapsed_time(t1)),
                 "h2d": host_noise[:, :nf].numel() * host_noise.element_size(),
-                "d2h": host_out.numel() * host_out.element_size()}
+                "d2h": (jpeg_bytes // max(1, steps) + 48) if jpeg else host_out.numel() * host_out.element_size()}
 
     streams = 1 if sp_mode else world           # independent video streams in flight
     main_run = measure(sp_mode, K, 42, profile_step=True)
@@ -571,6 +588,20 @@ def main():
         egress = {"value": streams * K * FRAMES_PER_STEP / (r["ms"] / 1e3), "unit": "frames/s",
                   "d2h_bytes_per_step": r["d2h"], "ms_per_step": r["ms"] / K,
                   "what": "e2e loop with kr_frames_to_rgb8 on the device and a uint8 [12,480,832,3] download"}
+
+    # and with the whole egress on the device (second half): kr_frames_to_jpeg writes the files the
+    # reference produces with Pillow in a 24-thread pool (byte-identical, tests/test_zz_jpeg_gpu.py); ~1-3 MB of JPEG
+    # bytes per block cross PCIe.  Never allowed to take the headline line down with it.
+    egress_jpeg = None
+    if not sp_mode and not args.no_egress:
+        try:
+            r = measure_e2e(False, K, 2542, jpeg=True)
+            egress_jpeg = {"value": streams * K * FRAMES_PER_STEP / (r["ms"] / 1e3), "unit": "frames/s",
+                           "d2h_bytes_per_step": r["d2h"], "ms_per_step": r["ms"] / K, "quality": 90,
+                           "what": "e2e loop with kr_frames_to_jpeg on the device (4 launches per block) and a download "
+                                   "of the 12 JPEG files' used bytes; files byte-identical to Pillow quality=90"}
+        except Exception as ex:  # noqa: BLE001
+            egress_jpeg = {"value": None, "error": f"{type(ex).__name__}: {ex}"[:200]}
 
     # FP8 tier (the reference's `enable_fp8: true`): same loop with the DiT block linears on the
     # kind::f8f6f4 GEMM + dynamic per-tensor activation casts.  Reported beside the bf16 headline, never instead of it.
@@ -638,6 +669,7 @@ def main():
                                   else "off (eager launches)",
                    "dit_tflop_per_step": block_tflop},
         "egress_rgb8": egress,
+        "egress_jpeg": egress_jpeg,
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": e2e_run["h2d"],
                 "d2h_bytes_per_step": e2e_run["d2h"], "ms_per_step": e2e_run["ms"] / K},
         "gpu_launches": main_run["launches"],
