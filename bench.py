@@ -503,6 +503,9 @@ def main():
                 px = sess.generate_block()
             e1.record()
             barrier()
+            if sp:
+                out["exchange"] = transformer.model.sp.exchange
+                out["exchange_note"] = transformer.model.sp.fallback_reason
             out["launches"] = ops.launch_count - n0
             out["clocks"] = clocks.stop() if rank == 0 else None
             out["ms"] = max_over_ranks(e0.elapsed_time(e1))
@@ -647,9 +650,10 @@ def main():
         except Exception as ex:  # noqa: BLE001
             cpu = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
     if sp_mode:
+        how = ("the rows<->heads exchange is done by the kernels over NVLink peer memory" if main_run.get("exchange") == "p2p"
+               else f"the rows<->heads exchange falls back to NCCL all-to-all ({main_run.get('exchange_note')})")
         par = (f"ONE stream on {world} GPUs: token rows sharded for all token-wise kernels, heads sharded for "
-               f"self-attention; the rows<->heads exchange is done by the kernels over NVLink peer memory "
-               f"(realtime_video_b200/parallel.py); VAE decode on rank 0")
+               f"self-attention; {how} (realtime_video_b200/parallel.py); VAE decode on rank 0")
     else:
         par = "1 GPU" if world == 1 else f"{world} independent replicas (no data-path collective)"
     line = {

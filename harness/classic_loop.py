@@ -55,8 +55,10 @@ class PipelineState(torch.nn.Module):
             # multi-GPU single-stream mode: the caches live in the rank's symmetric allocation so that the peers'
             # kernels can store K / V rows straight into them (realtime_video_b200/parallel.py)
             kv = sp.alloc_kv_cache(self.num_transformer_blocks, shape, dtype, device)
-            self.kv_cache1 = [dict(k=k, v=v, global_end_index=0, local_end_index=0) for k, v in kv]
-            return
+            if kv is not None:
+                self.kv_cache1 = [dict(k=k, v=v, global_end_index=0, local_end_index=0) for k, v in kv]
+                return
+            # symmetric memory unavailable: sp has switched to the collective exchange on every rank
         self.kv_cache1 = [dict(k=torch.zeros(shape, dtype=dtype, device=device),
                                v=torch.zeros(shape, dtype=dtype, device=device),
                                global_end_index=0, local_end_index=0) for _ in range(self.num_transformer_blocks)]

@@ -53,6 +53,7 @@ class SequenceParallel:
         self._used = 0
         self._ptr_cache = {}
         self._kv = self._kv_key = self._q_buf = self._o_rows_buf = self._o_heads_buf = None
+        self.fallback_reason = None  # set when the p2p setup failed and the collective exchange took over
 
     # -- sharding arithmetic -------------------------------------------------------------------
     def rows(self, L: int):
@@ -78,12 +79,28 @@ class SequenceParallel:
             if self._arena.numel() < nbytes:
                 raise RuntimeError("symmetric arena already created with a smaller size")
             return
-        import torch.distributed._symmetric_memory as symm_mem
         g = self.group if self.group is not None else dist.group.WORLD
-        self._arena = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
-        self._hdl = symm_mem.rendezvous(self._arena, g.group_name)
-        self._peer_base = [int(p) for p in self._hdl.buffer_ptrs]
-        assert self._peer_base[self.rank] == self._arena.data_ptr()
+        err = None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            arena = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+            hdl = symm_mem.rendezvous(arena, g.group_name)
+            peer_base = [int(p) for p in hdl.buffer_ptrs]
+            if peer_base[self.rank] != arena.data_ptr():
+                raise RuntimeError("symmetric-memory rendezvous returned a foreign base address for this rank")
+        except Exception as ex:  # noqa: BLE001 - any failure (no P2P access, allocator limits, ...) takes the fallback
+            err = ex
+        # the decision must be the same on every rank: one rank on the p2p path and another on collectives would hang
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            self.exchange = "nccl"
+            self.fallback_reason = f"{type(err).__name__}: {err}" if err is not None else "a peer rank failed"
+            import warnings
+            warnings.warn("SequenceParallel: symmetric-memory setup failed on at least one rank "
+                          f"({self.fallback_reason}); using the torch.distributed all-to-all exchange instead")
+            return
+        self._arena, self._hdl, self._peer_base = arena, hdl, peer_base
         self._used = 0
 
     def carve(self, shape, dtype) -> torch.Tensor:
@@ -119,7 +136,9 @@ class SequenceParallel:
 
     def alloc_kv_cache(self, num_layers: int, shape, dtype, device):
         """KV caches [1, rows, heads_local, head_dim] x 2 x layers plus the exchange buffers, all inside ONE symmetric
-        allocation created here (collective, once per object).  Returns [(k, v)] per layer, zero-filled."""
+        allocation created here (collective, once per object).  Returns [(k, v)] per layer, zero-filled — or None
+        when the symmetric-memory setup failed on any rank: the object has then switched (on every rank) to the
+        collective exchange and the caller allocates ordinary caches."""
         key = (num_layers, tuple(int(d) for d in shape), dtype)
         if self._arena is None:
             rows, hl, hd = key[1][1], key[1][2], key[1][3]
@@ -130,6 +149,8 @@ class SequenceParallel:
                 return (n + 255) // 256 * 256
             n_loc = rows // self.world + 8
             self.reserve(2 * num_layers * al(rows * dh * es) + al(rows * dh * es) + al(n_loc * D * es) + 4096, device)
+            if self._arena is None:          # setup failed on some rank: every rank is on the collective exchange now
+                return None
             self._kv = [(self.carve(key[1], dtype), self.carve(key[1], dtype)) for _ in range(num_layers)]
             self._q_buf = self.carve((rows, dh), dtype)                 # all rows, my heads (peers write)
             self._o_rows_buf = self.carve((n_loc, D), dtype)            # my rows, all heads (peers write)

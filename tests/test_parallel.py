@@ -116,3 +116,48 @@ def test_sequence_parallel_dit_schedule_gloo():
     ret = mgr.dict()
     mp.spawn(_sp_model_worker, args=(world, port, ret), nprocs=world, join=True)
     assert [ret.get(r) for r in range(world)] == ["ok"] * world
+
+
+def _fallback_worker(rank, world, port, ret):
+    """p2p setup failing on ONE rank only must move EVERY rank to the collective exchange (a split decision would
+    hang the first layer): rank 0 gets a working fake symmetric allocation, rank 1 raises."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import types
+        import warnings
+
+        import torch.distributed._symmetric_memory as symm_mem
+        from realtime_video_b200.parallel import SequenceParallel
+
+        def fake_empty(n, dtype=None, device=None):
+            if rank == 1:
+                raise RuntimeError("no peer access")
+            return torch.empty(n, dtype=dtype)
+
+        def fake_rendezvous(t, group_name):
+            return types.SimpleNamespace(buffer_ptrs=[t.data_ptr(), 0], barrier=lambda channel=0: None)
+
+        symm_mem.empty, symm_mem.rendezvous = fake_empty, fake_rendezvous
+        sp = SequenceParallel(exchange="p2p")
+        assert sp.p2p
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            kv = sp.alloc_kv_cache(2, (1, 48, 1, 128), torch.float32, "cpu")
+        assert kv is None and sp.exchange == "nccl" and not sp.p2p and sp.fallback_reason
+        assert any("symmetric-memory setup failed" in str(x.message) for x in w)
+        # the collective exchange works afterwards
+        x = torch.arange(24 * 256, dtype=torch.float32).view(24, 256)
+        r0, n = sp.rows(24)
+        assert torch.equal(sp.rows_to_heads(x[r0:r0 + n]), x[:, rank * 128:(rank + 1) * 128])
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_p2p_setup_failure_on_one_rank_falls_back_everywhere_gloo():
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_fallback_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert [ret.get(r) for r in range(2)] == ["ok"] * 2
