@@ -137,6 +137,18 @@ def _tile_for(H: int, W: int):
     return best[1], best[2]
 
 
+def _weights_tag(w: torch.Tensor):
+    """Identity of a parameter's current contents for the prepared-weights cache: storage address + version counter
+    (in-place updates such as ``load_state_dict`` bump it).  Inference tensors (a model built or cast under
+    ``torch.inference_mode()``) track no version — they cannot be updated in place outside inference mode either —
+    so the address alone identifies them."""
+    try:
+        ver = w._version
+    except RuntimeError:
+        ver = None
+    return (w.data_ptr(), ver)
+
+
 class _Conv:
     """Kernel-ready conv: weight [rows, taps*cin_pad], bias [n], taps, channel config, and (for
     temporal convs) the persistent input buffer whose two leading frames are the cache."""
@@ -195,7 +207,7 @@ class DecoderEngine:
 
     # -- weight preparation ---------------------------------------------------------------
     def _prepare(self, dtype, device, H, W):
-        key = (dtype, str(device), H, W, self.decoder.conv1.weight._version, self.decoder.conv1.weight.data_ptr())
+        key = (dtype, str(device), H, W, _weights_tag(self.decoder.conv1.weight))
         if self._key == key:
             return
         d = self.decoder
@@ -370,26 +382,25 @@ class DecoderEngine:
                         tc = b["tconv"]
                         y = self._new(2 * T, h, w, C)
                         frame = h * w * C
-                        if True:
-                            # chunk-wise cache update of vae_block3.py:55-62 per reference chunk
-                            step = self._chunk_frames(i)
-                            for s0 in range(0, T, step):
-                                xin = torch.cat([b["tcache"], x[s0:s0 + step]], dim=0)
-                                for half in range(2):
-                                    ops.vae_conv(xin, tc.weight[half * C:(half + 1) * C], tc.bias[half * C:],
-                                                 n=C, cout=C, T=step, taps=tc.taps, tile=_tile_for(h, w),
-                                                 out_raw=y[2 * s0 + half:], raw_frame_stride=2 * frame)
-                                xs = x[s0:s0 + step]
-                                if step >= 2:
-                                    b["tcache"].copy_(xs[-2:])
-                                elif self.single_mode:         # demo_utils/vae.py:106-111: [0, x]
-                                    b["tcache"][0].zero_()
-                                    b["tcache"][1].copy_(xs[0])
-                                else:
-                                    old_last = b["tcache"][1]
-                                    pad = torch.where(old_last == 0, torch.zeros_like(xs[0]), xs[0])
-                                    b["tcache"][0].copy_(pad)
-                                    b["tcache"][1].copy_(xs[0])
+                        # chunk-wise cache update of vae_block3.py:55-62 per reference chunk
+                        step = self._chunk_frames(i)
+                        for s0 in range(0, T, step):
+                            xin = torch.cat([b["tcache"], x[s0:s0 + step]], dim=0)
+                            for half in range(2):
+                                ops.vae_conv(xin, tc.weight[half * C:(half + 1) * C], tc.bias[half * C:],
+                                             n=C, cout=C, T=step, taps=tc.taps, tile=_tile_for(h, w),
+                                             out_raw=y[2 * s0 + half:], raw_frame_stride=2 * frame)
+                            xs = x[s0:s0 + step]
+                            if step >= 2:
+                                b["tcache"].copy_(xs[-2:])
+                            elif self.single_mode:         # demo_utils/vae.py:106-111: [0, x]
+                                b["tcache"][0].zero_()
+                                b["tcache"][1].copy_(xs[0])
+                            else:
+                                old_last = b["tcache"][1]
+                                pad = torch.where(old_last == 0, torch.zeros_like(xs[0]), xs[0])
+                                b["tcache"][0].copy_(pad)
+                                b["tcache"][1].copy_(xs[0])
                         x, T = y, 2 * T
                 up = ops.vae_upsample2x(x, self._new(T, 2 * h, 2 * w, C))
                 h, w = 2 * h, 2 * w
@@ -603,7 +614,7 @@ class EncoderEngine:
 
     def _prepare(self, dtype, device, H, W):
         e = self.encoder
-        key = (dtype, str(device), H, W, e.conv1.weight._version, e.conv1.weight.data_ptr())
+        key = (dtype, str(device), H, W, _weights_tag(e.conv1.weight))
         if self._key == key:
             return
         pc = lambda m, **kw: _prep_conv(m.weight.data, m.bias.data, dtype, device, **kw)  # noqa: E731

@@ -128,3 +128,18 @@ def test_classic_wrapper_encode_to_latent(g):
     assert lat.shape == (2, 3, 16, 8, 12) and lat.dtype == torch.float32
     assert rel_l2(lat[0], gs["cold9_64x96/mu"][0].permute(1, 0, 2, 3)) < TOL
     assert not torch.allclose(lat[0], lat[1])
+
+
+def test_decoder_built_and_cast_under_inference_mode(g):
+    """A module constructed / cast inside torch.inference_mode() has parameters that track no version counter
+    (``._version`` raises); the prepared-weights cache must not depend on it."""
+    from realtime_video_b200.vae import VAEDecoderWrapper
+    with torch.inference_mode():
+        m = VAEDecoderWrapper()
+        m.load_state_dict(synthetic_vae_params(seed=0), strict=False)
+        m = m.half().eval()
+        with pytest.raises(RuntimeError):
+            m.decoder.conv1.weight._version
+        px, cache = m(g["s8x12/z0"].half(), *([None] * 55))
+        px2, _ = m(g["s8x12/z1"].half(), *cache)
+    assert rel_l2(px, g["s8x12/px0"]) < TOL and rel_l2(px2, g["s8x12/px1"]) < TOL
