@@ -93,3 +93,21 @@ def test_register_and_stack_budget():
             assert stack == 0, (fn, reg, stack)
         if "attn_fwd_kernel" in fn:
             assert reg <= 168 and stack <= 64, (fn, reg, stack)
+
+
+def test_jpeg_kernels_keep_their_tables_out_of_local_memory(sass):
+    """kr_jpeg.cu: the per-block DCT keeps its 64 coefficients in registers (zigzag / quant-table indices fold to
+    constants after unrolling), the Huffman tables live in __constant__ memory built at compile time, the bit stream is
+    assembled with global OR-reductions and the per-frame prefix sums with warp shuffles."""
+    kern = {k: _ops(v) for k, v in sass.items() if "jpeg_" in k}
+    assert len(kern) == 5, sorted(kern)                       # dct (2 loaders), scan, emit, stuff
+    emit = next(v for k, v in kern.items() if "jpeg_emit" in k)
+    assert any(o.startswith(("RED", "ATOMG")) and ".OR" in o for o in emit)
+    for name in ("jpeg_scan", "jpeg_stuff"):
+        ops = next(v for k, v in kern.items() if name in k)
+        assert any(o.startswith("SHFL.UP") for o in ops), name
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", str(_lib.LIB_PATH)], capture_output=True, text=True,
+                         check=True).stdout
+    for m in re.finditer(r"Function (\S*jpeg_\S*):\s*\n\s*(.*)", out):
+        stack = int(re.search(r"STACK:(\d+)", m.group(2)).group(1))
+        assert stack <= 16, (m.group(1), stack)               # a spilled temporary at most; no local arrays
