@@ -596,7 +596,7 @@ def main():
     # reference produces with Pillow in a 24-thread pool (byte-identical, tests/test_zz_jpeg_gpu.py); ~1-3 MB of JPEG
     # bytes per block cross PCIe.  Never allowed to take the headline line down with it.
     egress_jpeg = None
-    if not sp_mode and not args.no_egress:
+    if world == 1 and not args.no_egress:          # one rank only: a caught failure must not desynchronise barriers
         try:
             r = measure_e2e(False, K, 2542, jpeg=True)
             egress_jpeg = {"value": streams * K * FRAMES_PER_STEP / (r["ms"] / 1e3), "unit": "frames/s",
