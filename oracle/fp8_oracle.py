@@ -1,5 +1,8 @@
-"""TEST INFRASTRUCTURE — CPU oracle for the FP8 linear (not shipped; only tests/ import it).  "parity unpinned":
-torchao is not in the image and the reference ships no FP8 vectors, so this restates the PUBLISHED algorithm of
+"""TEST INFRASTRUCTURE — CPU oracle for the FP8 linear (not shipped; only tests/ import it).  Parity PARTLY pinned:
+the scaled matmul + bias + bf16 rounding is pinned to ``torch._scaled_mm`` on the CPU — the kernel torchao's Float8
+linear dispatches to (tests/test_fp8_cpu.py::test_oracle_linear_matches_torch_scaled_mm); the per-tensor scale formula
+is "parity unpinned": torchao is not in the image and the reference ships no FP8 vectors, so it restates the PUBLISHED
+algorithm of
 ``Float8DynamicActivationFloat8WeightConfig(granularity=PerTensor())`` (torchao float8 inference: per-tensor
 ``scale = finfo(e4m3).max / clamp(amax, 1e-12)``; ``x_q = (x * scale).clamp(+-448).to(float8_e4m3fn)``;
 ``torch._scaled_mm(x_q, w_q.t(), scale_a = 1/scale_x, scale_b = 1/scale_w, bias, out_dtype = bf16)`` with fp32

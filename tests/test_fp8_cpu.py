@@ -91,3 +91,26 @@ def test_block_schedule_with_fp8_linears_tracks_the_bf16_schedule(monkeypatch):
     assert kv[0]["local_end_index"] == 3 * 96 and float(kv[0]["v"].abs().sum()) > 0
     r = rel_l2(got, ref)
     assert r < 0.15, r                               # two blocks of e4m3 linears on a 256-wide toy model
+
+
+@pytest.mark.parametrize("M,N,K", [(32, 48, 64), (96, 256, 512), (17, 128, 1024)])
+def test_oracle_linear_matches_torch_scaled_mm(M, N, K):
+    """torchao's Float8 dynamic-activation linear ends in ``torch._scaled_mm(x_q, w_q.t(), scale_a, scale_b, bias,
+    out_dtype=bf16)`` — the call the reference's `enable_fp8` path executes (release_server.py:179-182).  torchao itself
+    is absent here, but that kernel's semantics are available on the CPU: the oracle's scaled matmul + bias + bf16
+    rounding is pinned to it (the per-tensor scale formula stays a restatement of torchao's published algorithm)."""
+    if not hasattr(torch, "_scaled_mm"):
+        pytest.skip("torch._scaled_mm not available")
+    torch.manual_seed(M + N + K)
+    x, w, b = torch.randn(M, K) * 2, torch.randn(N, K) * 0.03, torch.randn(N)
+    xq, sx = F8.quantize_per_tensor(x)
+    wq, sw = F8.quantize_per_tensor(w)
+    try:
+        want = torch._scaled_mm(xq, wq.t(), scale_a=sx.reshape(1).float(), scale_b=sw.reshape(1).float(),
+                                bias=b.bfloat16(), out_dtype=torch.bfloat16)
+    except (RuntimeError, NotImplementedError) as ex:
+        pytest.skip(f"torch._scaled_mm unsupported on this CPU build: {ex}")
+    got = F8.linear_fp8(x, w, b.bfloat16())
+    assert got.dtype == want.dtype == torch.bfloat16
+    assert rel_l2(got.float(), want.float()) < 2e-3
+    assert (got == want).float().mean() > 0.98            # identical up to fp32 summation order before the bf16 rounding
