@@ -296,6 +296,36 @@ def _traffic_db() -> dict:
     return {}
 
 
+def _reference_host_egress_ms(px: torch.Tensor, reps: int = 2):
+    """The reference's own frame egress on this box's host cores, timed on the block just decoded: fp32 download to
+    pinned memory, ``add_(1).mul_(0.5).clamp_(0, 1)`` (release_server.py:979-983), then per frame
+    ``to_pil_image(...).save(JPEG, quality=90)`` in a 24-thread pool (release_server.py:945-946, :973)."""
+    try:
+        import io
+        from concurrent.futures import ThreadPoolExecutor
+
+        import torchvision.transforms.functional as TF
+        host = torch.empty(px.shape, dtype=torch.float32)
+        if px.is_cuda:
+            host = host.pin_memory()
+
+        def enc(frame):
+            buf = io.BytesIO()
+            TF.to_pil_image(frame, "RGB").save(buf, format="JPEG", quality=90)
+            return buf.getvalue()
+        with ThreadPoolExecutor(max_workers=24) as pool:
+            ts = []
+            for _ in range(reps + 1):
+                t0 = time.time()
+                host.copy_(px)
+                norm = host.add_(1.0).mul_(0.5).clamp_(0.0, 1.0)
+                list(pool.map(enc, [norm[0, i] for i in range(norm.shape[1])]))
+                ts.append(time.time() - t0)
+        return 1e3 * min(ts[1:])
+    except Exception:  # noqa: BLE001 - Pillow / torchvision missing: no host comparison
+        return None
+
+
 def run_vae_workload(args, dev, rank, world, barrier, max_over_ranks):
     """BASELINE configs[4]: VAE-decode-only throughput at 832x480.  One step = one steady block (3 latent frames ->
     12 pixel frames) of a running stream (warm feature cache); N > 1 = N independent streams (the decoder is one
@@ -571,7 +601,10 @@ def main():
                 torch.cuda.current_stream().synchronize()                                       # frames usable on host
             t1.record()
             barrier()
-        return {"ms": max_over_ranks(t0.elapsed_time(t1)),
+            host_ref_ms = None
+            if jpeg and decode:
+                host_ref_ms = _reference_host_egress_ms(px)
+        return {"ms": max_over_ranks(t0.elapsed_time(t1)), "host_ref_ms": host_ref_ms,
                 "h2d": host_noise[:, :nf].numel() * host_noise.element_size(),
                 "d2h": (jpeg_bytes // max(1, steps) + 48) if jpeg else host_out.numel() * host_out.element_size()}
 
@@ -601,8 +634,11 @@ def main():
             r = measure_e2e(False, K, 2542, jpeg=True)
             egress_jpeg = {"value": streams * K * FRAMES_PER_STEP / (r["ms"] / 1e3), "unit": "frames/s",
                            "d2h_bytes_per_step": r["d2h"], "ms_per_step": r["ms"] / K, "quality": 90,
+                           "reference_host_egress_ms_per_step": r["host_ref_ms"], "host_threads": 24,
                            "what": "e2e loop with kr_frames_to_jpeg on the device (4 launches per block) and a download "
-                                   "of the 12 JPEG files' used bytes; files byte-identical to Pillow quality=90"}
+                                   "of the 12 JPEG files' used bytes; files byte-identical to Pillow quality=90; "
+                                   "reference_host_egress_ms_per_step = the reference's own egress of one block (fp32 "
+                                   "download + normalise + Pillow in a 24-thread pool) timed on this box's host cores"}
         except Exception as ex:  # noqa: BLE001
             egress_jpeg = {"value": None, "error": f"{type(ex).__name__}: {ex}"[:200]}
 
