@@ -210,6 +210,45 @@ int kr_vae_scale_input(int dtype, const void* z, long zt, long zc, long zh, long
 int kr_softmax_rows(int dtype, const float* s, long ld, void* p, long ldo, int rows, int cols,
                     void* stream);
 
+/* One whole CausalWanAttentionBlock forward (causal_model.py:440-492: AdaLN-modulated self-attention with KV-cache
+ * append (:218-397), T5 cross-attention (model.py:171-228), GELU FFN) as ONE call: the same 14 launches, with the same
+ * arguments, as the per-op schedule above (kr_add_modulation, kr_ln_modulate, kr_gemm split into the V-cache slot,
+ * kr_qkv_norm_rope into the K-cache slot, kr_attn_fwd, kr_gemm gate+residual, kr_ln_modulate affine, kr_gemm,
+ * kr_rmsnorm, kr_attn_fwd over the prompt K/V, kr_gemm residual, kr_ln_modulate, kr_gemm GELU, kr_gemm gate+residual).
+ * bf16, fused to_qkv ([3D, D], causal_model.py:204-216), one GPU, prompt K/V already projected (crossattn_cache
+ * is_init); all weights [out, in] contiguous.  The cache index algebra of causal_model.py:349-392 stays with the
+ * caller, which passes the resolved slot: rows [local_start, local_end) of the K / V cache receive this call's keys /
+ * values; the queries attend rows [attn_lo, local_end) (cache branch, mask_mode 0) or rows [0, L) under the
+ * block-causal rule (recompute branch, mask_mode 1: block_len / window / pad_keys as in kr_attn_fwd).
+ * x [L, D] is updated in place.  workspace: kr_dit_block_workspace_bytes(L, D, ffn, frames) bytes, 256-byte aligned,
+ * private to the stream; gemm_workspace: optional stream-K workspace exactly as in kr_gemm_ws (may be NULL). */
+typedef struct KrDitBlockParams {
+  int L, D, ffn, heads, head_dim;          /* tokens of this call, model width, FFN width, heads, 128 */
+  int frames, rows_per_frame;              /* L == frames * rows_per_frame (modulation / gate rows change per frame) */
+  int grid_h, grid_w, start_frame;         /* RoPE positions: token grid and the absolute index of the first frame */
+  int cross_attn_norm;                     /* 1: norm3 is an affine LayerNorm, 0: identity */
+  float eps_block, eps_qk, eps_norm3, eps_cross;
+  void* x; int ldx;                        /* residual stream, in place */
+  const void* e0; int lde0_frame;          /* time projection [frames, 6, D]; elements between frames */
+  const void* modulation;                  /* blocks.N.modulation [6, D] */
+  const void* rope;                        /* float2 (cos, sin) [1024, 64] */
+  const void* w_qkv; const void* b_qkv;    /* self_attn.to_qkv */
+  const void* norm_q; const void* norm_k;  /* self_attn.norm_q / norm_k weights [D] */
+  const void* w_o; const void* b_o;        /* self_attn.o */
+  void* k_cache; void* v_cache; int ld_cache;   /* row 0 of this layer's caches viewed as [rows, D] */
+  int local_start, local_end, attn_lo;
+  int mask_mode, block_len, window, pad_keys;
+  const void* norm3_w; const void* norm3_b;
+  const void* w_cq; const void* b_cq; const void* norm_cq;      /* cross_attn.q, cross_attn.norm_q */
+  const void* ck; const void* cv; int ld_ck, ld_cv, text_len;   /* projected + normalised prompt K, V [text_len, D] */
+  const void* w_co; const void* b_co;      /* cross_attn.o */
+  const void* w_ffn0; const void* b_ffn0; const void* w_ffn2; const void* b_ffn2;
+  void* workspace; size_t workspace_bytes;
+  void* gemm_workspace; size_t gemm_workspace_bytes;
+} KrDitBlockParams;
+size_t kr_dit_block_workspace_bytes(int L, int D, int ffn, int frames);
+int kr_dit_block_fwd(const KrDitBlockParams* params, void* stream);
+
 /* Frame egress: decoder pixels fp32 [frames, 3, H, W] in [-1, 1] -> packed RGB bytes
  * [frames, H, W, 3], byte = trunc(clamp((x + 1) * 0.5, 0, 1) * 255) in fp32 — the arithmetic the reference
  * runs on the host after the device->host copy (release_server.py:979-983 `add_(1.0).mul_(0.5).clamp_(0,1)`,

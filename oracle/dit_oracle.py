@@ -116,7 +116,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask: Optional[
 class DiTConfig:
     def __init__(self, dim=5120, ffn_dim=13824, num_heads=40, num_layers=40, in_dim=16, out_dim=16,
                  freq_dim=256, text_dim=4096, text_len=512, eps=1e-6, local_attn_size=-1,
-                 sink_size=0, patch_size=(1, 2, 2), frame_seqlen_const=1560):
+                 sink_size=0, patch_size=(1, 2, 2), frame_seqlen_const=1560, cross_attn_norm=True):
         self.dim, self.ffn_dim, self.num_heads, self.num_layers = dim, ffn_dim, num_heads, num_layers
         self.in_dim, self.out_dim, self.freq_dim = in_dim, out_dim, freq_dim
         self.text_dim, self.text_len, self.eps = text_dim, text_len, eps
@@ -124,6 +124,8 @@ class DiTConfig:
         # the reference hard-codes 1560 tokens per latent frame (causal_model.py:192, :351)
         self.frame_seqlen_const = frame_seqlen_const
         self.head_dim = dim // num_heads
+        # norm3 = WanLayerNorm(affine) if cross_attn_norm else nn.Identity() (causal_model.py:424-426); True for every Wan 2.1 model
+        self.cross_attn_norm = cross_attn_norm
 
 
 def new_kv_cache(cfg: DiTConfig, size: int, dtype, device="cpu") -> List[Dict]:
@@ -234,7 +236,7 @@ class DiTOracle:
         h = (per_frame(layer_norm(x, cfg.eps)) * (1 + e[1]) + e[0]).flatten(0, 1)
         y = self.self_attn(i, h, grid, kv_cache, current_start, mask_args)
         x = x + (per_frame(y) * e[2]).flatten(0, 1)
-        h = layer_norm(x, cfg.eps, self.p[pre + "norm3.weight"], self.p[pre + "norm3.bias"])
+        h = layer_norm(x, cfg.eps, self.p[pre + "norm3.weight"], self.p[pre + "norm3.bias"]) if cfg.cross_attn_norm else x
         x = x + self.cross_attn(i, h, context, crossattn_cache)
         h = (per_frame(layer_norm(x, cfg.eps)) * (1 + e[4]) + e[3]).flatten(0, 1)
         y = self.lin(pre + "ffn.2", F.gelu(self.lin(pre + "ffn.0", h), approximate="tanh"))

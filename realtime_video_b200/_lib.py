@@ -16,7 +16,7 @@ from pathlib import Path
 _PKG_DIR = Path(__file__).resolve().parent
 _CSRC = _PKG_DIR / "csrc"
 LIB_PATH = _PKG_DIR / "libkrea_b200.so"
-SOURCES = ["kr_host.cu", "kr_gemm.cu", "kr_gemm2.cu", "kr_gemm_sk.cu", "kr_gemm_fp8.cu", "kr_attn.cu", "kr_t5attn.cu", "kr_dit_elem.cu", "kr_vae.cu", "kr_jpeg.cu", "kr_api.cu"]
+SOURCES = ["kr_host.cu", "kr_gemm.cu", "kr_gemm2.cu", "kr_gemm_sk.cu", "kr_gemm_fp8.cu", "kr_attn.cu", "kr_t5attn.cu", "kr_dit_elem.cu", "kr_vae.cu", "kr_jpeg.cu", "kr_dit_block.cu", "kr_api.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -89,6 +89,36 @@ _f = ctypes.c_float
 _l = ctypes.c_long
 _sz = ctypes.c_size_t
 
+
+
+class KrDitBlockParams(ctypes.Structure):
+    """``KrDitBlockParams`` of include/krea_b200.h, field for field."""
+    _fields_ = [
+        ("L", _i), ("D", _i), ("ffn", _i), ("heads", _i), ("head_dim", _i),
+        ("frames", _i), ("rows_per_frame", _i),
+        ("grid_h", _i), ("grid_w", _i), ("start_frame", _i),
+        ("cross_attn_norm", _i),
+        ("eps_block", _f), ("eps_qk", _f), ("eps_norm3", _f), ("eps_cross", _f),
+        ("x", _vp), ("ldx", _i),
+        ("e0", _vp), ("lde0_frame", _i),
+        ("modulation", _vp),
+        ("rope", _vp),
+        ("w_qkv", _vp), ("b_qkv", _vp),
+        ("norm_q", _vp), ("norm_k", _vp),
+        ("w_o", _vp), ("b_o", _vp),
+        ("k_cache", _vp), ("v_cache", _vp), ("ld_cache", _i),
+        ("local_start", _i), ("local_end", _i), ("attn_lo", _i),
+        ("mask_mode", _i), ("block_len", _i), ("window", _i), ("pad_keys", _i),
+        ("norm3_w", _vp), ("norm3_b", _vp),
+        ("w_cq", _vp), ("b_cq", _vp), ("norm_cq", _vp),
+        ("ck", _vp), ("cv", _vp), ("ld_ck", _i), ("ld_cv", _i), ("text_len", _i),
+        ("w_co", _vp), ("b_co", _vp),
+        ("w_ffn0", _vp), ("b_ffn0", _vp), ("w_ffn2", _vp), ("b_ffn2", _vp),
+        ("workspace", _vp), ("workspace_bytes", _sz),
+        ("gemm_workspace", _vp), ("gemm_workspace_bytes", _sz),
+    ]
+
+
 # name -> argtypes; every function returns int except where noted
 SIGNATURES = {
     "kr_gemm_kernel_id": [_i, _i, _i, _i],
@@ -120,6 +150,7 @@ SIGNATURES = {
     "kr_vae_scale_input": [_i, _vp, _l, _l, _l, _l, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "kr_softmax_rows": [_i, _vp, _l, _vp, _l, _i, _i, _vp],
     "kr_frames_to_rgb8": [_vp, _vp, _i, _i, _i, _vp],
+    "kr_dit_block_fwd": [ctypes.POINTER(KrDitBlockParams), _vp],
     "kr_frames_to_jpeg": [_vp, _i, _i, _i, _i, _vp, _l, _vp, _vp, _sz, _vp],
     "kr_rgb8_to_jpeg": [_vp, _i, _i, _i, _i, _vp, _l, _vp, _vp, _sz, _vp],
 }
@@ -144,6 +175,9 @@ def load() -> ctypes.CDLL:
         lib.kr_last_error.argtypes = []
         lib.kr_gemm_workspace_bytes.restype = _sz
         lib.kr_gemm_workspace_bytes.argtypes = []
+        if hasattr(lib, "kr_dit_block_workspace_bytes"):
+            lib.kr_dit_block_workspace_bytes.restype = _sz
+            lib.kr_dit_block_workspace_bytes.argtypes = [_i, _i, _i, _i]
         if hasattr(lib, "kr_jpeg_workspace_bytes"):
             lib.kr_jpeg_workspace_bytes.restype = _sz
             lib.kr_jpeg_workspace_bytes.argtypes = [_i, _i, _i]

@@ -19,6 +19,7 @@ There is no eager fallback: CPU tensors raise (ops._req).
 from __future__ import annotations
 
 import math
+import os
 import types
 from typing import Dict, List, Optional
 
@@ -185,6 +186,7 @@ class CausalWanModel(nn.Module):
         self._rope_angles = ang
         self._rope_table: Optional[torch.Tensor] = None      # device float32 (cos, sin)
         self.sp = None          # optional parallel.SequenceParallel (single-stream multi-GPU mode)
+        self.use_block_fwd = os.environ.get("KR_BLOCK_FWD", "0") not in ("", "0")   # one C-ABI call per block
         self.init_weights()
         self.gradient_checkpointing = False
         self.block_mask = None
@@ -238,19 +240,11 @@ class CausalWanModel(nn.Module):
         h = ops.gemm(ctx, te[0].weight, te[0].bias, epilogue=ops.EPI_BIAS_GELU)
         return ops.gemm(h, te[2].weight, te[2].bias)
 
-    def _self_attention(self, blk: CausalWanAttentionBlock, h, grid, kv_cache, current_start, mask):
-        """causal_model.py:218-397: projections, q/k RMSNorm, RoPE, cache write, attention.
-        The cache slot is resolved first so the fused QKV GEMM writes its V third straight into
-        the V cache (split output) and the RMSNorm+RoPE kernel writes K in place."""
-        sa = blk.self_attn
-        sp = self.sp
-        n_loc, D = h.shape                       # local token rows
-        L = n_loc if sp is None else n_loc * sp.world
-        r0 = 0 if sp is None else sp.rank * n_loc
-        heads = sa.num_heads if sp is None else sp.local_heads(sa.num_heads)
-        Dh = heads * sa.head_dim                 # cache row width on this rank
-        f, gh, gw = grid
-        fs = gh * gw
+    @staticmethod
+    def _cache_slot(sa: CausalWanSelfAttention, kv_cache, L: int, Dh: int, fs: int, current_start: int, mask):
+        """KV-cache index algebra of causal_model.py:305-392 for a call that appends L token rows: returns the cache
+        views [rows, Dh], the slot [local_start, local_end) this call writes, the RoPE start frame and the new global
+        end index; performs the rolling-window eviction (:358-373) when the slot would overflow."""
         kc = kv_cache["k"][0].view(-1, Dh)       # [cache_rows, heads_local*128]
         vc = kv_cache["v"][0].view(-1, Dh)
         kv_size = kc.shape[0]
@@ -274,6 +268,23 @@ class CausalWanModel(nn.Module):
             local_start = local_end - L
         if local_start < 0 or local_end > kv_size:
             raise RuntimeError(f"KV cache overflow: slot [{local_start}, {local_end}) of {kv_size}")
+        return kc, vc, local_start, local_end, start_frame, current_end
+
+    def _self_attention(self, blk: CausalWanAttentionBlock, h, grid, kv_cache, current_start, mask):
+        """causal_model.py:218-397: projections, q/k RMSNorm, RoPE, cache write, attention.
+        The cache slot is resolved first so the fused QKV GEMM writes its V third straight into
+        the V cache (split output) and the RMSNorm+RoPE kernel writes K in place."""
+        sa = blk.self_attn
+        sp = self.sp
+        n_loc, D = h.shape                       # local token rows
+        L = n_loc if sp is None else n_loc * sp.world
+        r0 = 0 if sp is None else sp.rank * n_loc
+        heads = sa.num_heads if sp is None else sp.local_heads(sa.num_heads)
+        Dh = heads * sa.head_dim                 # cache row width on this rank
+        f, gh, gw = grid
+        fs = gh * gw
+        kc, vc, local_start, local_end, start_frame, current_end = self._cache_slot(sa, kv_cache, L, Dh, fs,
+                                                                                    current_start, mask)
         k_slot, v_slot = kc[local_start:local_end], vc[local_start:local_end]
         if sp is not None and sp.p2p:
             # sequence-parallel, exchange done by the kernels: project MY rows (all heads); the RMSNorm+RoPE kernel
@@ -382,10 +393,51 @@ class CausalWanModel(nn.Module):
                 cache["k"], cache["v"] = k, v
         return ops.attention(q, k[0].reshape(-1, D), v[0].reshape(-1, D), heads=ca.num_heads)
 
+    # -- whole block as ONE C-ABI call (kr_dit_block_fwd) ---------------------------------------------------------
+    # Opt-in (KR_BLOCK_FWD=1 or ``model.use_block_fwd = True``): the C function issues exactly the launches of the
+    # per-op schedule below (tests/test_block_fwd_cpu.py compares the two launch sequences call by call); what changes
+    # is the host side — one ctypes crossing per block instead of 14 and no temporary tensors.
+    def _block_fwd_eligible(self, blk: CausalWanAttentionBlock, x, crossattn_cache) -> bool:
+        sa, ca = blk.self_attn, blk.cross_attn
+        return (self.sp is None and x.dtype == torch.bfloat16 and sa.fused_projections and (2 * self.dim) % 256 == 0
+                and sa.qk_norm and ca.qk_norm and crossattn_cache is not None and bool(crossattn_cache["is_init"])
+                and getattr(ops, "_prof", None) is None
+                and not any(hasattr(m, "_kr_fp8") for m in (sa.to_qkv, sa.o, ca.q, ca.o, blk.ffn[0], blk.ffn[2])))
+
+    def _block_one_call(self, blk: CausalWanAttentionBlock, x, e0, grid, kv_cache, crossattn_cache, current_start, mask):
+        sa, ca = blk.self_attn, blk.cross_attn
+        L, D = x.shape
+        _, gh, gw = grid
+        fs = gh * gw
+        kc, vc, local_start, local_end, start_frame, current_end = self._cache_slot(sa, kv_cache, L, D, fs,
+                                                                                    current_start, mask)
+        if mask is not None:
+            lo, block_len, window, pad = 0, mask.block_len, mask.window, math.ceil(L / 128) * 128 - L
+        else:
+            max_att = sa._max_attention_frames * fs if sa.local_attn_size == -1 else sa.local_attn_size * fs
+            lo, block_len, window, pad = max(0, local_end - max_att), 0, 0, 0
+        n3 = blk.norm3 if isinstance(blk.norm3, nn.LayerNorm) else None
+        ops.dit_block_fwd(
+            x, e0, blk.modulation, self._rope(x.device),
+            w_qkv=sa.to_qkv.weight, b_qkv=sa.to_qkv.bias, norm_q=sa.norm_q.weight, norm_k=sa.norm_k.weight,
+            w_o=sa.o.weight, b_o=sa.o.bias, k_cache=kc, v_cache=vc, local_start=local_start, local_end=local_end,
+            attn_lo=lo, norm3_w=None if n3 is None else n3.weight, norm3_b=None if n3 is None else n3.bias,
+            w_cq=ca.q.weight, b_cq=ca.q.bias, norm_cq=ca.norm_q.weight,
+            ck=crossattn_cache["k"][0].reshape(-1, D), cv=crossattn_cache["v"][0].reshape(-1, D),
+            w_co=ca.o.weight, b_co=ca.o.bias, w_ffn0=blk.ffn[0].weight, b_ffn0=blk.ffn[0].bias,
+            w_ffn2=blk.ffn[2].weight, b_ffn2=blk.ffn[2].bias, heads=sa.num_heads, rows_per_frame=fs, grid_h=gh,
+            grid_w=gw, start_frame=start_frame, eps_block=blk.eps, eps_qk=sa.eps,
+            eps_norm3=0.0 if n3 is None else n3.eps, eps_cross=ca.eps, block_len=block_len, window=window, pad_keys=pad)
+        kv_cache["global_end_index"] = current_end
+        kv_cache["local_end_index"] = local_end
+        return x
+
     def _block(self, blk: CausalWanAttentionBlock, x, e0, grid, ctx, kv_cache, crossattn_cache,
                current_start, mask):
         """causal_model.py:440-492; x [L, D] is updated in place."""
         fs = grid[1] * grid[2]
+        if self.use_block_fwd and self._block_fwd_eligible(blk, x, crossattn_cache):
+            return self._block_one_call(blk, x, e0, grid, kv_cache, crossattn_cache, current_start, mask)
         r0 = 0 if self.sp is None else self.sp.rank * x.shape[0]       # global index of my first row
         emod = ops.add_modulation(blk.modulation, e0)                    # [F, 6, D]
         h = ops.ln_modulate(x, eps=blk.eps, mod=emod, shift_idx=0, scale_idx=1, rows_per_frame=fs,
@@ -396,10 +448,10 @@ class CausalWanModel(nn.Module):
                  gate=emod[:, 2], rows_per_gate=fs, out=x, row_offset=r0)
         n3 = blk.norm3
         if isinstance(n3, nn.LayerNorm):
-            h = ops.ln_modulate(x, eps=n3.eps, weight=n3.weight, bias=n3.bias, out=h)
+            hc = ops.ln_modulate(x, eps=n3.eps, weight=n3.weight, bias=n3.bias, out=h)
         else:
-            h = x
-        y = self._cross_attention(blk, h, ctx, crossattn_cache)
+            hc = x          # cross_attn_norm=False: the residual stream itself; `h` stays the scratch buffer
+        y = self._cross_attention(blk, hc, ctx, crossattn_cache)
         ca = blk.cross_attn
         _linear(y, ca.o, epilogue=ops.EPI_BIAS_RES, residual=x, out=x)
         h = ops.ln_modulate(x, eps=blk.eps, mod=emod, shift_idx=3, scale_idx=4, rows_per_frame=fs, out=h,

@@ -6,6 +6,7 @@ no eager / CPU fallback on the product path.
 """
 from __future__ import annotations
 
+import ctypes
 import math
 from typing import Optional
 
@@ -174,6 +175,72 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     _lib.check(rc, "kr_gemm_ws")
     _count()
     return out
+
+
+_block_ws = {}
+
+
+def dit_block_fwd(x: torch.Tensor, e0: torch.Tensor, modulation: torch.Tensor, rope: torch.Tensor, *,
+                  w_qkv, b_qkv, norm_q, norm_k, w_o, b_o, k_cache: torch.Tensor, v_cache: torch.Tensor,
+                  local_start: int, local_end: int, attn_lo: int, norm3_w, norm3_b, w_cq, b_cq, norm_cq,
+                  ck: torch.Tensor, cv: torch.Tensor, w_co, b_co, w_ffn0, b_ffn0, w_ffn2, b_ffn2, heads: int,
+                  rows_per_frame: int, grid_h: int, grid_w: int, start_frame: int, eps_block: float, eps_qk: float,
+                  eps_norm3: float, eps_cross: float, block_len: int = 0, window: int = 0, pad_keys: int = 0) -> torch.Tensor:
+    """One whole DiT block (kr_dit_block_fwd): x [L, D] bf16 updated in place.  k_cache / v_cache: this layer's caches
+    viewed as [rows, D]; rows [local_start, local_end) receive this call's K / V; block_len > 0 selects the recompute
+    branch (block-causal rule over rows [0, L)), otherwise the queries attend rows [attn_lo, local_end).
+    ck / cv: projected prompt K / V [text_len, D].  The scratch workspace is cached per (device, stream, shape)."""
+    _req(x, "x", torch.bfloat16)
+    L, ldx = _rows2d(x, "x")
+    D = x.shape[-1]
+    ffn = w_ffn0.shape[0]
+    for name, w, shape in (("w_qkv", w_qkv, (3 * D, D)), ("w_o", w_o, (D, D)), ("w_cq", w_cq, (D, D)),
+                           ("w_co", w_co, (D, D)), ("w_ffn0", w_ffn0, (ffn, D)), ("w_ffn2", w_ffn2, (D, ffn))):
+        _req(w, name, torch.bfloat16)
+        if tuple(w.shape) != shape or not w.is_contiguous():
+            raise _lib.KreaB200Error(f"dit_block_fwd: {name} must be contiguous {shape}, got {tuple(w.shape)}")
+    for name, t in (("e0", e0), ("modulation", modulation), ("k_cache", k_cache), ("v_cache", v_cache), ("ck", ck),
+                    ("cv", cv)):
+        _req(t, name, torch.bfloat16)
+    _req(rope, "rope", torch.float32)
+    F = e0.shape[-3]
+    if e0.stride(-1) != 1 or e0.stride(-2) != D or e0.shape[-2] != 6:
+        raise _lib.KreaB200Error("dit_block_fwd: e0 must be [frames, 6, D] with contiguous rows")
+    _, ld_cache = _rows2d(k_cache, "k_cache")
+    if _rows2d(v_cache, "v_cache")[1] != ld_cache:
+        raise _lib.KreaB200Error("dit_block_fwd: K and V caches must share their row pitch")
+    text_len, ld_ck = _rows2d(ck, "ck")
+    _, ld_cv = _rows2d(cv, "cv")
+    lib = _lib.load()
+    stream = _stream()
+    need = lib.kr_dit_block_workspace_bytes(L, D, ffn, F)
+    key = (x.device.index, stream, L, D, ffn, F)
+    ws = _block_ws.get(key)
+    if ws is None:
+        if len(_block_ws) > 8:
+            _block_ws.clear()
+        raw = torch.empty(need + 256, dtype=torch.uint8, device=x.device)
+        off = (-raw.data_ptr()) % 256                 # the C side wants 256-byte alignment whatever the allocator gives
+        ws = _block_ws[key] = raw[off:off + need]
+    gws_ptr, gws_bytes = _gemm_workspace(x.device, stream)
+    p = _lib.KrDitBlockParams(
+        L=L, D=D, ffn=ffn, heads=heads, head_dim=D // heads, frames=F, rows_per_frame=rows_per_frame,
+        grid_h=grid_h, grid_w=grid_w, start_frame=start_frame, cross_attn_norm=0 if norm3_w is None else 1,
+        eps_block=eps_block, eps_qk=eps_qk, eps_norm3=eps_norm3, eps_cross=eps_cross,
+        x=x.data_ptr(), ldx=ldx, e0=e0.data_ptr(), lde0_frame=e0.stride(-3), modulation=modulation.data_ptr(),
+        rope=rope.data_ptr(), w_qkv=w_qkv.data_ptr(), b_qkv=_ptr(b_qkv), norm_q=norm_q.data_ptr(),
+        norm_k=norm_k.data_ptr(), w_o=w_o.data_ptr(), b_o=_ptr(b_o), k_cache=k_cache.data_ptr(),
+        v_cache=v_cache.data_ptr(), ld_cache=ld_cache, local_start=local_start, local_end=local_end, attn_lo=attn_lo,
+        mask_mode=1 if block_len > 0 else 0, block_len=block_len, window=window, pad_keys=pad_keys,
+        norm3_w=_ptr(norm3_w), norm3_b=_ptr(norm3_b), w_cq=w_cq.data_ptr(), b_cq=_ptr(b_cq),
+        norm_cq=norm_cq.data_ptr(), ck=ck.data_ptr(), cv=cv.data_ptr(), ld_ck=ld_ck, ld_cv=ld_cv, text_len=text_len,
+        w_co=w_co.data_ptr(), b_co=_ptr(b_co), w_ffn0=w_ffn0.data_ptr(), b_ffn0=_ptr(b_ffn0),
+        w_ffn2=w_ffn2.data_ptr(), b_ffn2=_ptr(b_ffn2), workspace=ws.data_ptr(), workspace_bytes=ws.numel(),
+        gemm_workspace=gws_ptr, gemm_workspace_bytes=gws_bytes)
+    rc = lib.kr_dit_block_fwd(ctypes.byref(p), stream)
+    _lib.check(rc, "kr_dit_block_fwd")
+    _count(14)
+    return x
 
 
 _fp8_scratch = {}

@@ -72,6 +72,24 @@ def test_cache_branch(g, fused):
     assert all(c["is_init"] for c in ca)
 
 
+def test_model_without_cross_attn_norm_keeps_the_residual_stream(g):
+    """cross_attn_norm=False: norm3 is nn.Identity (causal_model.py:424-426) and the cross-attention reads the residual
+    stream itself; the FFN pre-norm must NOT be written over it (regression: it used to be, through an aliased scratch
+    buffer).  No Wan 2.1 checkpoint uses this configuration, so the check is against the oracle with the same flag."""
+    from oracle import dit_oracle as O
+    m = build(g, cross_attn_norm=False)
+    w = weights(g, torch.float32)
+    orc = O.DiTOracle(O.DiTConfig(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=128,
+                                  frame_seqlen_const=FS, cross_attn_norm=False), w)
+    kv, ca = caches(m, 6 * FS)
+    kv_o = O.new_kv_cache(orc.cfg, 6 * FS, torch.float32)
+    ca_o = O.new_crossattn_cache(orc.cfg, torch.float32)
+    for xname, t, start in (("in/x0", 1000, 0), ("in/x2", 1000, 3 * FS)):
+        got = fwd(m, g, xname, t, kv, ca, start)
+        ref = orc.forward_inference(g[xname].float(), torch.full((3,), float(t)), g["in/ctx"].float(), kv_o, ca_o, start)
+        assert rel_l2(got, ref) < TOL
+
+
 def test_recompute_branch_with_block_mask_and_padded_keys(g):
     m = build(g)
     kv, ca = caches(m, 8 * FS)
