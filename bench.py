@@ -439,6 +439,9 @@ def main():
     ap.add_argument("--graphs", default="off", choices=["on", "off"],
                     help="replay each DiT pass as a CUDA graph (validated on one GPU, tests/test_server_loop_gpu.py; "
                          "NOT with the multi-GPU exchange inside the capture: an 8-GPU run with it on hung)")
+    ap.add_argument("--block-fwd", default="off", choices=["on", "off"],
+                    help="issue every DiT block as ONE C-ABI call (kr_dit_block_fwd; same launches, less host work; "
+                         "single-GPU bf16 passes with a warm prompt cache)")
     ap.add_argument("--watchdog-s", type=int, default=600, help=argparse.SUPPRESS)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -503,6 +506,7 @@ def main():
     pe = factory.synthetic_prompt_embeds(device=dev)
     sp_mode = world > 1 and args.parallel == "sp"
     use_graphs = args.graphs == "on"
+    transformer.model.use_block_fwd = args.block_fwd == "on"
 
     def measure(sp: bool, steps: int, seed: int, profile_step: bool):
         """W warm-up blocks, then ``steps`` timed blocks (CUDA events, barrier + synchronize on both sides, max over
@@ -707,6 +711,7 @@ def main():
                    "l2": "weights (28 GB/pass) and KV cache exceed the 126 MB L2 every step; no flush needed",
                    "cuda_graphs": "each DiT pass replayed as a CUDA graph (captured on its 2nd occurrence)" if use_graphs
                                   else "off (eager launches)",
+                   "block_fwd": "one kr_dit_block_fwd call per DiT block" if args.block_fwd == "on" else "per-op calls",
                    "dit_tflop_per_step": block_tflop},
         "egress_rgb8": egress,
         "egress_jpeg": egress_jpeg,
