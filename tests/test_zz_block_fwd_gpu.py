@@ -47,7 +47,9 @@ def test_one_call_engages_and_matches_at_14b_width():
     """d 5120 / 40 heads / ffn 13824, 3 frames of 1560 tokens against a 6-frame cache: the bench's block shape."""
     from realtime_video_b200.dit import CausalWanModel
     torch.manual_seed(3)
-    m = CausalWanModel(dim=5120, ffn_dim=13824, num_heads=40, num_layers=1).to(device="cuda", dtype=torch.bfloat16).eval()
+    with torch.device("cuda"):                    # initialise on the device like tests/test_real_geometry_gpu.py
+        m = CausalWanModel(dim=5120, ffn_dim=13824, num_heads=40, num_layers=1)
+    m = m.to(dtype=torch.bfloat16).eval()
     m.blocks[0].self_attn.fuse_projections()
     blk = m.blocks[0]
     fs, L, D = 1560, 4680, 5120
