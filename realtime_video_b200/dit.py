@@ -402,6 +402,9 @@ class CausalWanModel(nn.Module):
         return (self.sp is None and x.dtype == torch.bfloat16 and sa.fused_projections and (2 * self.dim) % 256 == 0
                 and sa.qk_norm and ca.qk_norm and crossattn_cache is not None and bool(crossattn_cache["is_init"])
                 and getattr(ops, "_prof", None) is None
+                # not inside a CUDA-graph capture: the scratch workspace is cached across calls and must not come from
+                # a capture's private memory pool
+                and not (x.is_cuda and torch.cuda.is_current_stream_capturing())
                 and not any(hasattr(m, "_kr_fp8") for m in (sa.to_qkv, sa.o, ca.q, ca.o, blk.ffn[0], blk.ffn[2])))
 
     def _block_one_call(self, blk: CausalWanAttentionBlock, x, e0, grid, kv_cache, crossattn_cache, current_start, mask):
