@@ -157,6 +157,9 @@ class CausalWanModel(nn.Module):
             raise NotImplementedError("i2v is outside the hot path (SURVEY.md §2 row 18)")
         if (dim // num_heads) != 128:
             raise NotImplementedError("attention kernel supports head_dim 128 (all Wan 2.1 models)")
+        if not qk_norm:
+            raise NotImplementedError("qk_norm=False: the RMSNorm is fused into the RoPE / KV-append kernel; every "
+                                      "Wan 2.1 checkpoint has qk_norm=True")
         self.config = types.SimpleNamespace(
             model_type=model_type, patch_size=patch_size, text_len=text_len, in_dim=in_dim, dim=dim,
             ffn_dim=ffn_dim, freq_dim=freq_dim, text_dim=text_dim, out_dim=out_dim,

@@ -138,6 +138,43 @@ def test_wrapper_flow_and_x0(g):
     check(x0[0], g, "wrapper/x0")
 
 
+def test_wrapper_batch_of_two_equals_two_single_calls(g):
+    """B > 1 (the classic pipeline accepts a batch of noise, pipeline/causal_inference.py:48-50): every sample uses its
+    own slice of the [B, rows, heads, 128] KV cache and its own prompt; results and cache contents must equal two
+    batch-1 calls, and the shared python indices advance once."""
+    from realtime_video_b200.wan_wrapper import WanDiffusionWrapper
+    w = WanDiffusionWrapper(model_name="synthetic", timestep_shift=5.0, is_causal=True,
+                            model_config=dict(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=128))
+    w.model.load_state_dict(weights(g, torch.float32), strict=False)
+    w = w.float().eval()
+    n, d = 2, 128
+    lat = torch.stack([g["in/x0"].float().permute(1, 0, 2, 3), g["in/x1"].float().permute(1, 0, 2, 3)]).contiguous()
+    ctx = torch.stack([g["in/ctx"].float(), g["in/ctx"].float().flip(0)])
+    ts = torch.ones(2, 3, dtype=torch.int64) * 750
+
+    def kv_cache(B):
+        return [{"k": torch.zeros(B, 6 * FS, n, d), "v": torch.zeros(B, 6 * FS, n, d), "global_end_index": 0,
+                 "local_end_index": 0} for _ in w.model.blocks]
+
+    def ca_cache(B):
+        return [{"k": torch.zeros(B, 512, n, d), "v": torch.zeros(B, 512, n, d), "is_init": False} for _ in w.model.blocks]
+
+    kv2 = kv_cache(2)
+    with torch.no_grad():
+        flow2, x02 = w(noisy_image_or_video=lat, conditional_dict={"prompt_embeds": ctx}, timestep=ts, kv_cache=kv2,
+                       crossattn_cache=ca_cache(2), current_start=0)
+    assert flow2.shape == lat.shape
+    for b in range(2):
+        kv1 = kv_cache(1)
+        with torch.no_grad():
+            flow1, x01 = w(noisy_image_or_video=lat[b:b + 1], conditional_dict={"prompt_embeds": ctx[b:b + 1]},
+                           timestep=ts[b:b + 1], kv_cache=kv1, crossattn_cache=ca_cache(1), current_start=0)
+        assert torch.equal(flow2[b], flow1[0]) and torch.equal(x02[b], x01[0])
+        for c2, c1 in zip(kv2, kv1):
+            assert torch.equal(c2["k"][b], c1["k"][0]) and torch.equal(c2["v"][b], c1["v"][0])
+            assert (c2["global_end_index"], c2["local_end_index"]) == (c1["global_end_index"], c1["local_end_index"])
+
+
 def test_classic_inference_loop_host_logic_vs_reference():
     """CausalInferencePipeline.inference (2 blocks x (4 denoise + 1 context) passes with re-noising) on the CPU
     against the UNMODIFIED reference pipeline (tests/golden/pipeline_small.npz): cache allocation, per-block
