@@ -427,9 +427,10 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--parallel", default="sp", choices=["replicas", "sp"],
+    ap.add_argument("--parallel", default="sp", choices=["replicas", "sp", "pp"],
                     help="N>1 headline: ONE stream sequence-parallel over all GPUs (default, strong scaling; "
-                         "realtime_video_b200/parallel.py) or N independent replicas (weak scaling)")
+                         "realtime_video_b200/parallel.py), N independent replicas (weak scaling), or pp = ONE stream "
+                         "with the DiT layers sharded over the GPUs (BASELINE configs[2]: capacity, not latency)")
     ap.add_argument("--workload", default="block", choices=["block", "vae_decode"])
     ap.add_argument("--layers", type=int, default=LAYERS, help=argparse.SUPPRESS)      # debugging only
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
@@ -504,19 +505,24 @@ def main():
     vae_enc = factory.synthetic_vae_encoder(device=dev)
     models = harness.build_models(transformer, vae_decoder=vae, device=dev, vae_encoder=vae_enc)
     pe = factory.synthetic_prompt_embeds(device=dev)
-    sp_mode = world > 1 and args.parallel == "sp"
+    sp_mode = world > 1 and args.parallel in ("sp", "pp")      # ONE stream on all GPUs (sequence- or layer-sharded)
+    pp_mode = world > 1 and args.parallel == "pp"
     use_graphs = args.graphs == "on"
     transformer.model.use_block_fwd = args.block_fwd == "on"
 
     def measure(sp: bool, steps: int, seed: int, profile_step: bool):
         """W warm-up blocks, then ``steps`` timed blocks (CUDA events, barrier + synchronize on both sides, max over
         ranks); optionally ONE more block with per-launch events for the kernel split."""
-        if sp:
+        if sp and pp_mode:
+            from realtime_video_b200.parallel import LayerPipeline
+            if transformer.model.pp is None:
+                transformer.model.pp = LayerPipeline()
+        elif sp:
             from realtime_video_b200.parallel import SequenceParallel
             if transformer.model.sp is None:
                 transformer.model.sp = SequenceParallel()
         else:
-            transformer.model.sp = None
+            transformer.model.sp = transformer.model.pp = None
         decode = (not sp) or rank == 0              # one stream -> one VAE decode (rank 0)
         transformer.use_cuda_graphs = use_graphs and sp == sp_mode
         transformer._graphs = {}
@@ -537,7 +543,7 @@ def main():
                 px = sess.generate_block()
             e1.record()
             barrier()
-            if sp:
+            if sp and not pp_mode:
                 out["exchange"] = transformer.model.sp.exchange
                 out["exchange_note"] = transformer.model.sp.fallback_reason
             out["launches"] = ops.launch_count - n0
@@ -689,7 +695,11 @@ def main():
             cpu = cpu_reference_sample()
         except Exception as ex:  # noqa: BLE001
             cpu = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
-    if sp_mode:
+    if pp_mode:
+        par = (f"ONE stream on {world} GPUs, DiT layers sharded {LAYERS}/{world} per GPU (BASELINE configs[2]): residual "
+               f"stream handed GPU i -> i+1 with one NCCL send/recv per pass (47.9 MB), head output broadcast; stages run "
+               f"one after another, so this is the capacity configuration, not a latency one; VAE decode on rank 0")
+    elif sp_mode:
         how = ("the rows<->heads exchange is done by the kernels over NVLink peer memory" if main_run.get("exchange") == "p2p"
                else f"the rows<->heads exchange falls back to NCCL all-to-all ({main_run.get('exchange_note')})")
         par = (f"ONE stream on {world} GPUs: token rows sharded for all token-wise kernels, heads sharded for "

@@ -63,7 +63,8 @@ class GenerationSession:
     def __init__(self, params: GenerateParams, models: Models, prompt_embeds: Optional[torch.Tensor] = None,
                  device=None, decode: bool = True):
         self.params, self.models, self.decode = params, models, decode
-        self.decode_enabled = decode or getattr(models.pipeline.generator.model, "sp", None) is not None
+        # one stream on several GPUs (sequence-parallel or layer-pipelined): rank 0 decodes for everybody
+        self.decode_enabled = decode or self._multi_gpu_mode(models) is not None
         self.gpu = torch.device(device if device is not None else "cuda")
         self.width, self.height = params.width // 8 * 8, params.height // 8 * 8
         self.latent_width, self.latent_height = self.width // 8, self.height // 8
@@ -84,6 +85,12 @@ class GenerationSession:
         self.denoising_step_list = get_denoising_schedule(self.zero_padded_timesteps, params.strength,
                                                           steps=params.num_denoising_steps)
         self.last_pred = None
+
+    @staticmethod
+    def _multi_gpu_mode(models):
+        m = models.pipeline.generator.model
+        sp, pp = getattr(m, "sp", None), getattr(m, "pp", None)
+        return sp if sp is not None else pp
 
     # release_server.py:542-560
     def init_models(self):
@@ -118,13 +125,14 @@ class GenerationSession:
             z = frame.transpose(0, 1).unsqueeze(0)                        # [1, 3, 1, H, W] (v2v.py:138-158)
             mu, _ = self.models.vae_encoder(z, [None] * 55, stream=False)
             first = mu.squeeze(0).to(torch.float16).transpose(0, 1)[None].to(self.all_latents)   # [1,1,16,h,w]
-        sp = getattr(self.models.pipeline.generator.model, "sp", None)
-        if sp is not None:                                                # one stream on several GPUs
+        par = self._multi_gpu_mode(self.models)
+        if par is not None:                                               # one stream on several GPUs
             import torch.distributed as dist
             if first is None:
                 first = torch.empty_like(ctx[:, :1])
             first = first.contiguous()
-            dist.broadcast(first, src=0, group=sp.group)
+            src = 0 if par.group is None else dist.get_global_rank(par.group, 0)
+            dist.broadcast(first, src=src, group=par.group)
         return torch.cat((first, ctx), dim=1)
 
     # release_server.py:588-633

@@ -189,6 +189,7 @@ class CausalWanModel(nn.Module):
         self._rope_angles = ang
         self._rope_table: Optional[torch.Tensor] = None      # device float32 (cos, sin)
         self.sp = None          # optional parallel.SequenceParallel (single-stream multi-GPU mode)
+        self.pp = None          # optional parallel.LayerPipeline (layer-sharded multi-GPU mode, BASELINE configs[2])
         self.use_block_fwd = os.environ.get("KR_BLOCK_FWD", "0") not in ("", "0")   # one C-ABI call per block
         self.init_weights()
         self.gradient_checkpointing = False
@@ -491,19 +492,33 @@ class CausalWanModel(nn.Module):
         te, tp = self.time_embedding, self.time_projection
         e = ops.gemm(ops.activation(ops.gemm(emb, te[0].weight, te[0].bias), "silu"), te[2].weight, te[2].bias)
         e0 = ops.gemm(ops.activation(e, "silu"), tp[1].weight, tp[1].bias).view(Fr, 6, self.dim)
-        need_text = crossattn_cache is None or not all(c["is_init"] for c in crossattn_cache)
+        pp = self.pp
+        if pp is not None and self.sp is not None:
+            raise RuntimeError("layer pipeline and sequence parallelism are alternative multi-GPU modes")
+        lo, hi = (0, len(self.blocks)) if pp is None else pp.layers(len(self.blocks))
+        mine = range(lo, hi)                          # the blocks this rank runs (all of them on one GPU)
+        need_text = crossattn_cache is None or not all(crossattn_cache[i]["is_init"] for i in mine)
         ctx = self._embed_text(context) if need_text else None
         mask = self.block_mask
-        for i, blk in enumerate(self.blocks):
-            xs = self._block(blk, xs, e0, grid, ctx, kv_cache[i],
+        if pp is not None and not pp.first:
+            xs = pp.recv_from_previous(xs)            # residual stream after the previous stage's layers
+        for i in mine:
+            xs = self._block(self.blocks[i], xs, e0, grid, ctx, kv_cache[i],
                              crossattn_cache[i] if crossattn_cache is not None else None,
                              current_start, mask)
+        if pp is not None and not pp.last:
+            pp.send_to_next(xs)
         # head (causal_model.py:512-523, :951)
         fs = grid[1] * grid[2]
-        ehead = ops.add_modulation(self.head.modulation, e.view(Fr, 1, self.dim).expand(Fr, 2, self.dim).contiguous())
-        h = ops.ln_modulate(xs, eps=self.head.eps, mod=ehead, shift_idx=0, scale_idx=1, rows_per_frame=fs,
-                            row_offset=r0)
-        out = ops.gemm(h, self.head.head.weight, self.head.head.bias)
+        if pp is None or pp.last:
+            ehead = ops.add_modulation(self.head.modulation, e.view(Fr, 1, self.dim).expand(Fr, 2, self.dim).contiguous())
+            h = ops.ln_modulate(xs, eps=self.head.eps, mod=ehead, shift_idx=0, scale_idx=1, rows_per_frame=fs,
+                                row_offset=r0)
+            out = ops.gemm(h, self.head.head.weight, self.head.head.bias)
+        else:
+            out = torch.empty(xs.shape[0], self.head.head.weight.shape[0], dtype=xs.dtype, device=xs.device)
+        if pp is not None:
+            out = pp.broadcast_from_last(out)        # every rank carries the denoising loop on
         if self.sp is not None:
             out = self.sp.gather_rows(out)           # every rank needs the full latent for the next step
         return out, grid

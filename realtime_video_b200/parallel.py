@@ -199,3 +199,52 @@ class SequenceParallel:
         out = torch.empty(self.world * x.shape[0], *x.shape[1:], dtype=x.dtype, device=x.device)
         dist.all_gather_into_tensor(out, x.contiguous(), group=self.group)
         return out
+
+
+class LayerPipeline:
+    """BASELINE configs[2] as written: the DiT blocks sharded BY LAYER over the GPUs of one box (40 layers -> 5 per GPU
+    on 8 GPUs), the residual stream handed from GPU i to GPU i+1 with one point-to-point transfer per pass
+    (``torch.distributed`` send / recv: NCCL over NVLink on GPUs, gloo in the CPU tests).  Every rank keeps the KV and
+    prompt caches of its own layers only; the time / text embeddings are recomputed on every rank (two small GEMMs)
+    instead of being shipped; the last rank runs the head and broadcasts the [L, 64] result so that every rank can
+    carry the denoising loop on.
+
+    This is the capacity configuration (weights and caches of 1/N of the layers per GPU), NOT a latency one: the
+    stages of one stream run one after another, so a single stream gains nothing (SURVEY.md 8e option 1 says so);
+    the sequence-parallel mode above is the one that scales a stream.  Hand-off per pass: (N - 1) x 47.9 MB."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised before LayerPipeline()")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def layers(self, num_layers: int):
+        """[lo, hi) of the layers this rank owns (contiguous, as even as possible, earlier ranks take the remainder)."""
+        base, extra = divmod(num_layers, self.world)
+        lo = self.rank * base + min(self.rank, extra)
+        return lo, lo + base + (1 if self.rank < extra else 0)
+
+    def _global(self, r: int) -> int:
+        return r if self.group is None else dist.get_global_rank(self.group, r)
+
+    @property
+    def first(self) -> bool:
+        return self.rank == 0
+
+    @property
+    def last(self) -> bool:
+        return self.rank == self.world - 1
+
+    def recv_from_previous(self, x: torch.Tensor) -> torch.Tensor:
+        """Overwrite ``x`` (contiguous) with the residual stream the previous stage produced."""
+        dist.recv(x, src=self._global(self.rank - 1), group=self.group)
+        return x
+
+    def send_to_next(self, x: torch.Tensor) -> None:
+        dist.send(x.contiguous(), dst=self._global(self.rank + 1), group=self.group)
+
+    def broadcast_from_last(self, x: torch.Tensor) -> torch.Tensor:
+        dist.broadcast(x, src=self._global(self.world - 1), group=self.group)
+        return x

@@ -161,3 +161,60 @@ def test_p2p_setup_failure_on_one_rank_falls_back_everywhere_gloo():
     ret = mgr.dict()
     mp.spawn(_fallback_worker, args=(2, port, ret), nprocs=2, join=True)
     assert [ret.get(r) for r in range(2)] == ["ok"] * 2
+
+
+def _pp_model_worker(rank, world, port, ret):
+    """BASELINE configs[2]: the DiT layers sharded over the ranks (LayerPipeline), residual stream sent rank -> rank + 1,
+    head on the last rank, result broadcast.  Golden 2-layer model on 2 gloo ranks (one layer each), kernels replaced
+    by the fp32 stand-ins: every rank must return the reference's fp32 goldens, and each rank may only have touched
+    the caches of ITS layer."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import realtime_video_b200.dit as dit
+        from realtime_video_b200.parallel import LayerPipeline
+        from tests import cpu_ops_emulation as emu
+        from tests.golden_io import load_npz, rel_l2, weights
+        dit.ops = emu
+        g = load_npz("dit_small.npz")
+        FS = 96
+        m = dit.CausalWanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=128)
+        m.load_state_dict(weights(g, torch.float32), strict=False)
+        m = m.float().eval()
+        m.pp = LayerPipeline()
+        assert m.pp.layers(2) == (rank, rank + 1) and m.pp.layers(5) == ((0, 3) if rank == 0 else (3, 5))
+        n, d = 2, m.dim // m.num_heads
+        kv = [{"k": torch.zeros(1, 6 * FS, n, d), "v": torch.zeros(1, 6 * FS, n, d),
+               "global_end_index": 0, "local_end_index": 0} for _ in m.blocks]
+        ca = [{"k": torch.zeros(1, 512, n, d), "v": torch.zeros(1, 512, n, d), "is_init": False} for _ in m.blocks]
+
+        def fwd(xname, t, start):
+            x = g[xname].float()
+            with torch.no_grad():
+                return m(x[None], t=torch.full((1, x.shape[1]), float(t)), context=g["in/ctx"].float()[None],
+                         seq_len=32760, kv_cache=kv, crossattn_cache=ca, current_start=start)[0]
+
+        for xname, t, start, name in (("in/x0", 1000, 0, "cache/flow1"), ("in/x1", 750, 0, "cache/flow2"),
+                                      ("in/x2", 1000, 3 * FS, "cache/flow3")):
+            r = rel_l2(fwd(xname, t, start), g[f"fp32/{name}"])
+            assert r < 1e-4, (name, r)
+        mine, other = rank, 1 - rank
+        assert ca[mine]["is_init"] and not ca[other]["is_init"]
+        assert kv[mine]["local_end_index"] == 6 * FS and kv[other]["local_end_index"] == 0
+        assert float(kv[other]["k"].abs().max()) == 0.0 and float(kv[mine]["k"].abs().max()) > 0.0
+        if rank == 0:
+            assert rel_l2(kv[0]["k"][0], g["fp32/cache/k0"]) < 1e-4
+        else:
+            assert rel_l2(kv[1]["v"][0], g["fp32/cache/v1"]) < 1e-4
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_layer_pipeline_dit_schedule_gloo():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_pp_model_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert [ret.get(r) for r in range(world)] == ["ok"] * world
