@@ -326,6 +326,63 @@ def _reference_host_egress_ms(px: torch.Tensor, reps: int = 2):
         return None
 
 
+def assemble_line(args, world, sp_mode, pp_mode, use_graphs, main_run, e2e_run, egress, egress_jpeg, fp8_line, secondary,
+                  cpu) -> dict:
+    """The ONE JSON line of the block workload from the measured pieces (pure: no GPU, unit-tested on the CPU in
+    tests/test_bench_line_cpu.py so that a key error cannot cost a finished multi-minute run its result)."""
+    K, W = args.steps, args.warmup
+    streams = 1 if sp_mode else world
+    ms = main_run["ms"]
+    value = streams * K * FRAMES_PER_STEP / (ms / 1e3)
+    e2e = streams * K * FRAMES_PER_STEP / (e2e_run["ms"] / 1e3)
+    peaks = measured_peaks()
+    roofline = _flat_roofline(main_run["prof"], main_run["ms_prof"], peaks, _traffic_db())
+    block_tflop = (4 * LAYERS * layer_flops(LQ, LKV) + LAYERS * layer_flops(LQ, LQ)) / 1e12 * (args.layers / LAYERS)
+    if pp_mode:
+        par = (f"ONE stream on {world} GPUs, DiT layers sharded {LAYERS}/{world} per GPU (BASELINE configs[2]): residual "
+               f"stream handed GPU i -> i+1 with one NCCL send/recv per pass (47.9 MB), head output broadcast; stages run "
+               f"one after another, so this is the capacity configuration, not a latency one; VAE decode on rank 0")
+    elif sp_mode:
+        how = ("the rows<->heads exchange is done by the kernels over NVLink peer memory" if main_run.get("exchange") == "p2p"
+               else f"the rows<->heads exchange falls back to NCCL all-to-all ({main_run.get('exchange_note')})")
+        par = (f"ONE stream on {world} GPUs: token rows sharded for all token-wise kernels, heads sharded for "
+               f"self-attention; {how} (realtime_video_b200/parallel.py); VAE decode on rank 0")
+    else:
+        par = "1 GPU" if world == 1 else f"{world} independent replicas (no data-path collective)"
+    line = {
+        "metric": "frames_per_second_832x480_4step_t2v", "value": value, "unit": "frames/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+        "scaling": "strong" if sp_mode else "weak", "vs_baseline": (value / 11.0) if world == 1 else None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "dims": "Wan2.1-T2V-14B (40 layers, d 5120, ffn 13824, 40 heads)"
+                   if args.layers == LAYERS else f"DEBUG {args.layers} layers",
+                   "resolution": "832x480", "denoise_steps": 4, "kv_cache_num_frames": 3, "frames_per_step": 12,
+                   "passes_per_step": "1-frame VAE encode + 1 KV recompute + 4 denoise DiT passes + VAE decode (fp16)",
+                   "first_frame": "re-encoded from the oldest cached pixel frame once the window slides "
+                                  "(reference default keep_first_frame=False, release_server.py:571-576)",
+                   "parallelism": par,
+                   "l2": "weights (28 GB/pass) and KV cache exceed the 126 MB L2 every step; no flush needed",
+                   "cuda_graphs": "each DiT pass replayed as a CUDA graph (captured on its 2nd occurrence)" if use_graphs
+                                  else "off (eager launches)",
+                   "block_fwd": "one kr_dit_block_fwd call per DiT block" if args.block_fwd == "on" else "per-op calls",
+                   "dit_tflop_per_step": block_tflop},
+        "egress_rgb8": egress,
+        "egress_jpeg": egress_jpeg,
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": e2e_run["h2d"],
+                "d2h_bytes_per_step": e2e_run["d2h"], "ms_per_step": e2e_run["ms"] / K},
+        "gpu_launches": main_run["launches"],
+        "clocks": main_run["clocks"],
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "baseline_note": "vs_baseline = value / 11 fps (reference README.md:31: 11 fps on 1x B200, 4 steps); null for N>1 (nothing published)",
+    }
+    if secondary is not None:
+        line[secondary["mode"]] = secondary
+    if fp8_line is not None:
+        line["fp8"] = fp8_line
+    return line
+
+
 def run_vae_workload(args, dev, rank, world, barrier, max_over_ranks):
     """BASELINE configs[4]: VAE-decode-only throughput at 832x480.  One step = one steady block (3 latent frames ->
     12 pixel frames) of a running stream (warm feature cache); N > 1 = N independent streams (the decoder is one
@@ -620,10 +677,7 @@ def main():
 
     streams = 1 if sp_mode else world           # independent video streams in flight
     main_run = measure(sp_mode, K, 42, profile_step=True)
-    ms = main_run["ms"]
-    value = streams * K * FRAMES_PER_STEP / (ms / 1e3)
     e2e_run = measure_e2e(sp_mode, K, 1042)
-    e2e = streams * K * FRAMES_PER_STEP / (e2e_run["ms"] / 1e3)
 
     # same end-to-end loop with the byte egress kernel: kr_frames_to_rgb8 does the reference's
     # host-side normalise + to_pil_image conversion on the device, so uint8 [12,H,W,3] (14.4 MB) instead of fp32
@@ -686,57 +740,14 @@ def main():
         dist.destroy_process_group()
     if rank != 0:
         return
-    peaks = measured_peaks()
-    roofline = _flat_roofline(main_run["prof"], main_run["ms_prof"], peaks, _traffic_db())
-    block_tflop = (4 * LAYERS * layer_flops(LQ, LKV) + LAYERS * layer_flops(LQ, LQ)) / 1e12 * (args.layers / LAYERS)
     cpu = None
     if not args.no_cpu_baseline:
         try:
             cpu = cpu_reference_sample()
         except Exception as ex:  # noqa: BLE001
             cpu = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
-    if pp_mode:
-        par = (f"ONE stream on {world} GPUs, DiT layers sharded {LAYERS}/{world} per GPU (BASELINE configs[2]): residual "
-               f"stream handed GPU i -> i+1 with one NCCL send/recv per pass (47.9 MB), head output broadcast; stages run "
-               f"one after another, so this is the capacity configuration, not a latency one; VAE decode on rank 0")
-    elif sp_mode:
-        how = ("the rows<->heads exchange is done by the kernels over NVLink peer memory" if main_run.get("exchange") == "p2p"
-               else f"the rows<->heads exchange falls back to NCCL all-to-all ({main_run.get('exchange_note')})")
-        par = (f"ONE stream on {world} GPUs: token rows sharded for all token-wise kernels, heads sharded for "
-               f"self-attention; {how} (realtime_video_b200/parallel.py); VAE decode on rank 0")
-    else:
-        par = "1 GPU" if world == 1 else f"{world} independent replicas (no data-path collective)"
-    line = {
-        "metric": "frames_per_second_832x480_4step_t2v", "value": value, "unit": "frames/s",
-        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
-        "scaling": "strong" if sp_mode else "weak", "vs_baseline": (value / 11.0) if world == 1 else None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "dims": "Wan2.1-T2V-14B (40 layers, d 5120, ffn 13824, 40 heads)"
-                   if args.layers == LAYERS else f"DEBUG {args.layers} layers",
-                   "resolution": "832x480", "denoise_steps": 4, "kv_cache_num_frames": 3, "frames_per_step": 12,
-                   "passes_per_step": "1-frame VAE encode + 1 KV recompute + 4 denoise DiT passes + VAE decode (fp16)",
-                   "first_frame": "re-encoded from the oldest cached pixel frame once the window slides "
-                                  "(reference default keep_first_frame=False, release_server.py:571-576)",
-                   "parallelism": par,
-                   "l2": "weights (28 GB/pass) and KV cache exceed the 126 MB L2 every step; no flush needed",
-                   "cuda_graphs": "each DiT pass replayed as a CUDA graph (captured on its 2nd occurrence)" if use_graphs
-                                  else "off (eager launches)",
-                   "block_fwd": "one kr_dit_block_fwd call per DiT block" if args.block_fwd == "on" else "per-op calls",
-                   "dit_tflop_per_step": block_tflop},
-        "egress_rgb8": egress,
-        "egress_jpeg": egress_jpeg,
-        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": e2e_run["h2d"],
-                "d2h_bytes_per_step": e2e_run["d2h"], "ms_per_step": e2e_run["ms"] / K},
-        "gpu_launches": main_run["launches"],
-        "clocks": main_run["clocks"],
-        "roofline": roofline,
-        "cpu_baseline": cpu,
-        "baseline_note": "vs_baseline = value / 11 fps (reference README.md:31: 11 fps on 1x B200, 4 steps); null for N>1 (nothing published)",
-    }
-    if secondary is not None:
-        line[secondary["mode"]] = secondary
-    if fp8_line is not None:
-        line["fp8"] = fp8_line
+    line = assemble_line(args, world, sp_mode, pp_mode, use_graphs, main_run, e2e_run, egress, egress_jpeg, fp8_line,
+                         secondary, cpu)
     emit(line)
 
 
