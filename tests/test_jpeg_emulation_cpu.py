@@ -127,3 +127,33 @@ def test_python_op_argument_plumbing_with_the_emulator_behind_the_abi(emu, monke
     img = images(32, 48)["smooth"]
     out, sizes = ops.frames_to_jpeg(torch.from_numpy(img)[None], 75)
     assert ops.jpeg_files(out, sizes) == [pillow_jpeg(img, 75)]
+
+
+def test_random_images_sizes_and_qualities_property(emu):
+    """Property test: for random image content (noise mixed with flat regions and saturated pixels), random sizes
+    (multiples of 16) and every quality from 1 to 100, the emulated device encoder, the oracle and Pillow agree on
+    every byte."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(h=st.integers(1, 4), w=st.integers(1, 5), quality=st.integers(1, 100), seed=st.integers(0, 2 ** 31 - 1),
+           kind=st.sampled_from(["noise", "flat+noise", "saturated", "lines"]), threads=st.sampled_from([1024, 96, 5]))
+    def check(h, w, quality, seed, kind, threads):
+        H, W = 16 * h, 16 * w
+        rng = np.random.default_rng(seed)
+        img = (rng.random((H, W, 3)) * 256).astype(np.uint8)
+        if kind == "flat+noise":
+            img[: H // 2] = rng.integers(0, 256, 3, dtype=np.uint8)
+        elif kind == "saturated":
+            img = np.where(rng.random((H, W, 3)) < 0.5, 0, 255).astype(np.uint8)
+        elif kind == "lines":
+            img[:] = 128
+            img[::3] = 255
+            img[:, ::5] = 0
+        img = np.ascontiguousarray(img)
+        files, _, _, _ = run(emu, img[None], 1, quality, threads)
+        want = pillow_jpeg(img, quality)
+        assert files[0] == want and jpeg_oracle.encode_rgb8(img, quality) == want
+
+    check()
