@@ -16,8 +16,12 @@ ROOT = Path(__file__).resolve().parent.parent
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_p2p_and_nccl_exchange_are_bit_identical_to_one_gpu():
+    import socket
+    with socket.socket() as sock:                # a free port: the box may run other rendezvous
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29531", str(ROOT / "tools" / "check_sp.py")],
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(ROOT / "tools" / "check_sp.py")],
                        capture_output=True, text=True, timeout=300, cwd=str(ROOT))
     out = r.stdout + r.stderr
     assert r.returncode == 0 and out.count("SP CHECK PASS") == 2, out[-3000:]
