@@ -70,8 +70,12 @@ for exchange in ("p2p", "nccl"):
     hl = m.kv_cache_heads
     if exchange == "p2p":
         kvs = m.sp.alloc_kv_cache(len(m.blocks), (1, 6 * FS, hl, 128), torch.bfloat16, torch.device("cuda", local))
-        _, ca2 = caches(m, 6 * FS, hl)
-        kv2 = [{"k": k, "v": v, "global_end_index": 0, "local_end_index": 0} for k, v in kvs]
+        if kvs is None:       # symmetric memory unavailable: every rank has fallen back to the collective exchange
+            print(f"rank {rank}: p2p setup failed ({m.sp.fallback_reason}); checking the fallback exchange instead")
+            kv2, ca2 = caches(m, 6 * FS, hl)
+        else:
+            _, ca2 = caches(m, 6 * FS, hl)
+            kv2 = [{"k": k, "v": v, "global_end_index": 0, "local_end_index": 0} for k, v in kvs]
     else:
         kv2, ca2 = caches(m, 6 * FS, hl)
     got = run(m, kv2, ca2)
