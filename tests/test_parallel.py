@@ -218,3 +218,52 @@ def test_layer_pipeline_dit_schedule_gloo():
     ret = mgr.dict()
     mp.spawn(_pp_model_worker, args=(world, port, ret), nprocs=world, join=True)
     assert [ret.get(r) for r in range(world)] == ["ok"] * world
+
+
+def _pp_session_worker(rank, world, port, ret):
+    """The server block loop (harness.GenerationSession) with the DiT layer-pipelined over 2 gloo ranks: rank 0 decodes
+    and re-encodes the first context frame for everybody (broadcast), both ranks must carry the same latents as a
+    single process, block by block, through the sliding window."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import realtime_video_b200.dit as dit
+        import realtime_video_b200.vae as vae
+        import realtime_video_b200.wan_wrapper as ww
+        from realtime_video_b200.parallel import LayerPipeline
+        from tests import cpu_ops_emulation as emu
+        for mod in (dit, ww, vae):
+            mod.ops = emu
+        from tests.test_session_host_cpu import make
+
+        def run(pipelined):
+            sess, _ = make(keep_first_frame=False, decode=(not pipelined) or rank == 0, seed=11, blocks=3)
+            model = sess.models.pipeline.generator.model
+            model.pp = LayerPipeline() if pipelined else None
+            if pipelined:           # the session was built before the mode was set: recompute what depends on it
+                sess.decode_enabled = True
+            outs = []
+            for _ in range(3):          # block 2 is the first one behind the sliding window (first-frame re-encode)
+                out = sess.generate_block()
+                outs.append((out, sess.all_latents.clone()))
+            return outs
+
+        single = run(False)
+        piped = run(True)
+        for b, ((o1, lat1), (o2, lat2)) in enumerate(zip(single, piped)):
+            assert torch.equal(lat1, lat2), f"block {b}: latents differ on rank {rank}"
+            if rank == 0:
+                assert torch.equal(o1, o2), f"block {b}: pixels differ"
+            else:
+                assert o2.shape[-3] == 16            # non-decoding ranks hand back the latents of the block
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_layer_pipeline_server_loop_gloo():
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_pp_session_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert [ret.get(r) for r in range(2)] == ["ok"] * 2
