@@ -143,3 +143,27 @@ def test_decoder_built_and_cast_under_inference_mode(g):
         px, cache = m(g["s8x12/z0"].half(), *([None] * 55))
         px2, _ = m(g["s8x12/z1"].half(), *cache)
     assert rel_l2(px, g["s8x12/px0"]) < TOL and rel_l2(px2, g["s8x12/px1"]) < TOL
+
+
+@pytest.mark.parametrize("split", [(1, 1, 1, 1, 1), (2, 3), (4, 1), (5,)])
+def test_decode_is_independent_of_how_the_stream_is_chunked(g, split):
+    """Five latent frames decoded in one call, one by one, or in uneven calls: the causal decoder must produce the same
+    17 pixel frames (1 + 4 * 4) — chunk boundaries (MAX_CHUNK = 3, first-frame special case, feature-cache roll, the
+    up3d time_conv cache incl. its one-frame `where` quirk) may not show."""
+    z = torch.cat([g["s8x12/z0"], g["s8x12/z1"]], dim=1)[:, :5].half()          # [1, 5, 16, 8, 12]
+
+    def decode(parts):
+        m = decoder()
+        cache, outs, i = [None] * 55, [], 0
+        with torch.no_grad():
+            for n in parts:
+                px, cache = m(z[:, i:i + n], *cache)
+                outs.append(px)
+                i += n
+        return torch.cat(outs, dim=1)
+
+    ref = decode((3, 2))                       # the server's pattern for these goldens: block 0, then the next frames
+    got = decode(split)
+    assert got.shape == ref.shape == (1, 17, 3, 64, 96)
+    assert rel_l2(got, ref) < 1e-3, rel_l2(got, ref)
+    assert rel_l2(ref[:, :9], g["s8x12/px0"]) < TOL
