@@ -192,7 +192,61 @@ def _vae_attention(b, x):
     return out
 
 
-class DecoderEngine:
+class _CacheList(list):
+    """The feature-cache list handed to the caller: a plain ``list`` that can be weakly referenced."""
+    __slots__ = ("__weakref__",)
+
+
+class _StreamLedger:
+    """VALUE semantics for the feature-cache lists at zero cost in the common case.
+
+    The reference's cache entries are values: a caller may keep the list of one stream, run another stream through the
+    same module and come back (the server shares its models between WebSocket sessions, release_server.py:760).  Here
+    the entries handed out are VIEWS of the engine's own conv-input buffers (no copy, and passing them back is free).
+    Copy-on-conflict keeps that honest: the engine remembers (weakly) the last list it handed out; the moment a
+    DIFFERENT state arrives — a new stream (all None) or tensors that are not these buffers — the remembered list's
+    entries are replaced, in place, by clones of the buffers before anything is overwritten.  So a list never goes stale,
+    a single stream never pays a copy, and interleaved streams pay one snapshot + one restore per switch."""
+
+    _outstanding = None          # weakref to the last _CacheList handed out
+
+    def _views(self) -> List[Optional[torch.Tensor]]:        # engine: the buffers' cache frames, list positions fixed
+        raise NotImplementedError
+
+    def _hand_out(self) -> List[Optional[torch.Tensor]]:
+        import weakref
+        lst = _CacheList(self._views())
+        self._outstanding = weakref.ref(lst)
+        return lst
+
+    def _detach_outstanding(self) -> None:
+        """Another state is about to replace the buffers: give the list that still aliases them its own copy."""
+        ref, self._outstanding = self._outstanding, None
+        lst = ref() if ref is not None else None
+        if lst is None:
+            return
+        for i, (t, mine) in enumerate(zip(lst, self._views())):
+            if t is not None and mine is not None and t.data_ptr() == mine.data_ptr():
+                lst[i] = t.clone()
+
+    def _take_in(self, cache, what: str) -> bool:
+        """Make the buffers hold the state ``cache`` describes.  Returns False for a fresh stream (all None)."""
+        if cache is None or all(c is None for c in cache):
+            self._detach_outstanding()
+            return False
+        mine = self._views()
+        pairs = [(src, dst) for src, dst in zip(cache, mine) if dst is not None]
+        if any(src is None for src, _ in pairs):
+            raise ValueError(f"partial VAE feature cache: pass back the list this {what} returned")
+        if any(src.data_ptr() != dst.data_ptr() for src, dst in pairs):
+            self._detach_outstanding()       # foreign state (another stream's snapshot, a caller's clone): restore it
+            for src, dst in pairs:
+                if src.data_ptr() != dst.data_ptr():
+                    dst.copy_(src.reshape(dst.shape))
+        return True
+
+
+class DecoderEngine(_StreamLedger):
     """Runs VAEDecoder3d (+ the wrapper's un-scale and conv2) on the sm_100a kernels."""
 
     MAX_CHUNK = 3          # latent frames per launch sequence
@@ -271,6 +325,7 @@ class DecoderEngine:
 
     def reset(self):
         """Forget the stream: zero caches, first-frame state."""
+        self._detach_outstanding()
         self.conv1.buf.zero_()
         for b in self.blocks:
             if b["kind"] == "res":
@@ -283,6 +338,10 @@ class DecoderEngine:
 
     # -- cache export / import (opaque to the caller, tensors so that .to() works) -----------
     def export_cache(self) -> List[Optional[torch.Tensor]]:
+        """The 55-slot list for the caller (views of the buffers; see _StreamLedger for the aliasing contract)."""
+        return self._hand_out()
+
+    def _views(self) -> List[Optional[torch.Tensor]]:
         out: List[Optional[torch.Tensor]] = [None] * 55
         out[0] = self.conv1.buf[:2]
         i = 1
@@ -297,17 +356,9 @@ class DecoderEngine:
         return out
 
     def import_cache(self, cache: List[Optional[torch.Tensor]]):
-        if cache is None or all(c is None for c in cache):
+        if not self._take_in(cache, "decoder"):
             self.reset()
             return
-        mine = self.export_cache()
-        for src, dst in zip(cache, mine):
-            if dst is None:
-                continue
-            if src is None:
-                raise ValueError("partial VAE feature cache: pass back the list this decoder returned")
-            if src.data_ptr() != dst.data_ptr():
-                dst.copy_(src.reshape(dst.shape))
         self.initialised = True
 
     # -- one conv with fused epilogue --------------------------------------------------------
@@ -451,7 +502,7 @@ class DecoderEngine:
         zt = z[0]
         dtype = zt.dtype if zt.dtype in (torch.float16, torch.bfloat16) else torch.float16
         self._prepare(dtype, zt.device, zt.shape[-2], zt.shape[-1])
-        mine = [c for c in self.export_cache() if c is not None]
+        mine = [c for c in self._views() if c is not None]
         if len(feat_cache) != len(mine):
             raise ValueError(f"expected {len(mine)} cache tensors, got {len(feat_cache)}")
         for src, dst in zip(feat_cache, mine):
@@ -462,7 +513,7 @@ class DecoderEngine:
                 dst[..., :src.shape[-1]].copy_(src)
         first = bool(is_first_frame.item()) if torch.is_tensor(is_first_frame) else bool(is_first_frame)
         pix = self.decode_chunk(zt.to(dtype), first=first)
-        return pix[None].to(z.dtype), [c for c in self.export_cache() if c is not None]
+        return pix[None].to(z.dtype), [c for c in self._views() if c is not None]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -481,7 +532,7 @@ def _register_decoder(mod) -> int:
 @torch.library.custom_op("krea_b200::vae_decode_stream", mutates_args=())
 def _vae_decode_stream(z: torch.Tensor, first: bool, handle: int) -> List[torch.Tensor]:
     mod = _DECODERS[handle]()
-    px, _ = mod._decode(z, [None] * 55 if first else mod.engine.export_cache())
+    px, _ = mod._decode(z, [None] * 55 if first else mod.engine._views())
     mod._stream_calls = getattr(mod, "_stream_calls", 0) + 1
     return [px, torch.full((1,), mod._stream_calls, dtype=torch.int64, device=z.device)]
 
@@ -542,7 +593,7 @@ class VAEDecoderWrapper(nn.Module):
             return px, [token] + [None] * 54
         cache = list(feat_cache)
         if cache and cache[0] is not None and cache[0].dtype == torch.int64:      # token from a compiled call
-            cache = self.engine.export_cache()
+            cache = self.engine._views()
         return self._decode(z, cache)
 
 
@@ -597,7 +648,7 @@ class Encoder3d(nn.Module):
                                   CausalConv3d(out_dim, z_dim, 3, padding=1))
 
 
-class EncoderEngine:
+class EncoderEngine(_StreamLedger):
     """Encoder3d + WanVAE_.conv1 + latent scaling on the sm_100a kernels, streaming like the reference
     (demo_utils/vae_block3.py:141-175 over wan/modules/vae.py:301-345): the first chunk is ONE pixel frame on
     an empty cache (every causal conv sees zero history, the downsample3d time_convs are skipped and only
@@ -677,25 +728,24 @@ class EncoderEngine:
 
     def reset(self):
         """Forget the stream: zero history frames (frames >= 2 of a buffer are rewritten before every use)."""
+        self._detach_outstanding()
         for c in self._cache_tensors():
             c.zero_()
         self.initialised = False
 
-    def export_cache(self) -> List[Optional[torch.Tensor]]:
-        """The reference's 55-slot list (24 used by the encoder); entries are this engine's own buffers."""
+    def _views(self) -> List[Optional[torch.Tensor]]:
         mine = self._cache_tensors()
         return mine + [None] * (55 - len(mine))
 
+    def export_cache(self) -> List[Optional[torch.Tensor]]:
+        """The reference's 55-slot list (24 used by the encoder); entries are views of this engine's own buffers
+        (see _StreamLedger for the aliasing contract)."""
+        return self._hand_out()
+
     def import_cache(self, cache):
-        if cache is None or all(c is None for c in cache):
+        if not self._take_in(cache, "encoder"):
             self.reset()
             return
-        mine = self._cache_tensors()
-        for src, dst in zip(cache, mine):
-            if src is None:
-                raise ValueError("partial VAE feature cache: pass back the list this encoder returned")
-            if src.data_ptr() != dst.data_ptr():
-                dst.copy_(src.reshape(dst.shape))
         self.initialised = True
 
     def _conv(self, c: _Conv, T, src=None, **kw):

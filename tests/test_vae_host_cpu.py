@@ -167,3 +167,73 @@ def test_decode_is_independent_of_how_the_stream_is_chunked(g, split):
     assert got.shape == ref.shape == (1, 17, 3, 64, 96)
     assert rel_l2(got, ref) < 1e-3, rel_l2(got, ref)
     assert rel_l2(ref[:, :9], g["s8x12/px0"]) < TOL
+
+
+def test_two_interleaved_streams_on_one_decoder_have_value_semantics(g):
+    """The reference's feature caches are values: one module can serve several streams whose callers keep their own
+    cache lists (the server shares its models between sessions, release_server.py:760).  Here the lists alias the
+    engine's buffers — copy-on-conflict must make that invisible: streams A and B interleaved on ONE module produce what
+    two separate modules produce, and a single stream never pays a copy."""
+    za0, za1, za2 = g["s8x12/z0"].half(), g["s8x12/z1"].half(), g["s8x12/z2"].half()
+    zb0, zb1 = (za1[:, :3] * 0.5).contiguous(), (za0 * -0.7).contiguous()
+
+    def alone(zs):
+        m, cache, outs = decoder(), [None] * 55, []
+        with torch.no_grad():
+            for z in zs:
+                px, cache = m(z, *cache)
+                outs.append(px)
+        return outs
+
+    want_a, want_b = alone([za0, za1, za2]), alone([zb0, zb1])
+    m = decoder()
+    with torch.no_grad():
+        a0, ca = m(za0, *([None] * 55))
+        views = [t.data_ptr() for t in ca if t is not None]
+        b0, cb = m(zb0, *([None] * 55))                        # stream B starts: A's list must become a snapshot
+        assert all(t.data_ptr() != p for t, p in zip([t for t in ca if t is not None], views))
+        a1, ca = m(za1, *ca)                                   # back to A: B's list snapshotted, A restored
+        b1, cb = m(zb1, *cb)
+        a2, ca = m(za2, *ca)
+    for got, want in zip((a0, a1, a2), want_a):
+        assert torch.equal(got, want)
+    for got, want in zip((b0, b1), want_b):
+        assert torch.equal(got, want)
+    # single stream: the list handed out IS the buffers (no copy), and passing it back costs nothing
+    m2 = decoder()
+    with torch.no_grad():
+        _, c1 = m2(za0, *([None] * 55))
+        p1 = [t.data_ptr() for t in c1 if t is not None]
+        _, c2 = m2(za1, *c1)
+    assert [t.data_ptr() for t in c2 if t is not None] == p1 and [t.data_ptr() for t in c1 if t is not None] == p1
+
+
+def test_interleaved_encoder_streams_have_value_semantics(g):
+    from realtime_video_b200.vae import VAEEncoderWrapper
+    torch.manual_seed(0)
+
+    def encoder():
+        from oracle.vae_oracle import synthetic_vae_params
+        torch.manual_seed(0)                      # conv1 (WanVAE_.conv1) keeps its random init: same in every instance
+        m = VAEEncoderWrapper()
+        sd = synthetic_vae_params(seed=0)
+        m.encoder.load_state_dict({k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}, strict=False)
+        return m.half().eval()
+
+    fa, fb = torch.rand(1, 3, 9, 64, 96).half() * 2 - 1, torch.rand(1, 3, 9, 64, 96).half() * 2 - 1
+
+    def alone(f):
+        m = encoder()
+        with torch.no_grad():
+            mu0, c = m(f[:, :, :5], [None] * 55, stream=False)
+            mu1, c = m(f[:, :, 5:], c, stream=True)
+        return mu0, mu1
+
+    wa, wb = alone(fa), alone(fb)
+    m = encoder()
+    with torch.no_grad():
+        a0, ca = m(fa[:, :, :5], [None] * 55, stream=False)
+        b0, cb = m(fb[:, :, :5], [None] * 55, stream=False)
+        a1, ca = m(fa[:, :, 5:], ca, stream=True)
+        b1, cb = m(fb[:, :, 5:], cb, stream=True)
+    assert torch.equal(a0, wa[0]) and torch.equal(a1, wa[1]) and torch.equal(b0, wb[0]) and torch.equal(b1, wb[1])
