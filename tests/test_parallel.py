@@ -56,7 +56,7 @@ def _worker(rank, world, port, L, heads, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,L,heads", [(2, 24, 4), (4, 40, 4)])
+@pytest.mark.parametrize("world,L,heads", [(2, 24, 4), (4, 40, 4), (8, 64, 8)])
 def test_rows_heads_all_to_all_gloo(world, L, heads):
     port = _free_port()
     mgr = mp.Manager()
