@@ -14,7 +14,7 @@
 namespace {
 std::string g_log;
 void rec(const char* fmt, ...) {
-  char buf[1024];
+  char buf[3072];
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(buf, sizeof(buf), fmt, ap);
@@ -56,13 +56,20 @@ int ln_modulate(const void* x, int ldx, void* out, int ldo, int rows, int D, flo
   return KR_OK;
 }
 int qkv_post(const QkvPostParams& p, int rows, cudaStream_t stream) {
+  char peers[1024] = "";
+  if (p.peer_cols > 0) {           // sequence-parallel exchange: the per-rank destination pointers
+    int n = 0;
+    for (int i = 0; i < 8; ++i)
+      n += snprintf(peers + n, sizeof(peers) - n, " qp%d=%p kp%d=%p vp%d=%p", i, static_cast<void*>(p.q_peer[i]), i,
+                    static_cast<void*>(p.k_peer[i]), i, static_cast<void*>(p.v_peer[i]));
+  }
   rec("qkv_post q=%p ldq=%d k=%p ldk=%d v=%p ldv=%d wq=%p wk=%p q_out=%p ldqo=%d k_out=%p ldko=%d v_out=%p ldvo=%d "
-      "rope=%p rows=%d D=%d head_dim=%d grid_h=%d grid_w=%d start_frame=%d row_offset=%d eps=%.9g peer_cols=%d stream=%p",
+      "rope=%p rows=%d D=%d head_dim=%d grid_h=%d grid_w=%d start_frame=%d row_offset=%d eps=%.9g peer_cols=%d stream=%p%s",
       static_cast<const void*>(p.q), p.ldq, static_cast<const void*>(p.k), p.ldk, static_cast<const void*>(p.v), p.ldv,
       static_cast<const void*>(p.wq), static_cast<const void*>(p.wk), static_cast<void*>(p.q_out), p.ldqo,
       static_cast<void*>(p.k_out), p.ldko, static_cast<void*>(p.v_out), p.ldvo, static_cast<const void*>(p.rope), rows,
       p.D, p.head_dim, p.grid_h, p.grid_w, p.start_frame, p.row_offset, static_cast<double>(p.eps), p.peer_cols,
-      static_cast<void*>(stream));
+      static_cast<void*>(stream), peers);
   return KR_OK;
 }
 int rmsnorm_rows(const void* x, int ldx, void* out, int ldo, const void* w, int rows, int D, float eps,
@@ -92,7 +99,15 @@ int gemm_fp8_tn(int, const void*, int, const void*, int, const GemmParams&, cons
   return KR_OK;
 }
 int t5_attn(const void*, int, const void*, int, const void*, int, const T5AttnParams&, cudaStream_t) { rec("t5_attn"); return KR_OK; }
-int p2p_scatter_rows(const void*, int, void* const*, int, int, int, int, int, cudaStream_t) { rec("p2p_scatter_rows"); return KR_OK; }
+int p2p_scatter_rows(const void* src, int ld_src, void* const* dst_peer, int ld_dst, int rows, int cols, int rows_per_peer,
+                     int world, cudaStream_t stream) {
+  char peers[512] = "";
+  int n = 0;
+  for (int i = 0; i < world && i < 8; ++i) n += snprintf(peers + n, sizeof(peers) - n, " dp%d=%p", i, dst_peer[i]);
+  rec("p2p_scatter_rows src=%p ld_src=%d ld_dst=%d rows=%d cols=%d rows_per_peer=%d world=%d stream=%p%s", src, ld_src,
+      ld_dst, rows, cols, rows_per_peer, world, static_cast<void*>(stream), peers);
+  return KR_OK;
+}
 int activation(const void*, void*, size_t, int, cudaStream_t) { rec("activation"); return KR_OK; }
 int patchify(const void*, long, long, long, long, void*, int, int, int, int, cudaStream_t) { rec("patchify"); return KR_OK; }
 int unpatchify_x0(const void*, int, const void*, const double*, void*, void*, int, int, int, int, cudaStream_t) {

@@ -271,3 +271,100 @@ def test_argument_validation(reclib):
     assert reclib.kr_dit_block_fwd(ctypes.byref(p), None) == -1 and b"kr_dit_block_fwd" in reclib.kr_last_error()
     assert reclib.kr_dit_block_workspace_bytes(4680, 5120, 13824, 3) >= 4680 * (5 * 5120 + 13824) * 2 + 3 * 6 * 5120 * 2
     assert reclib.kr_dit_block_workspace_bytes(0, 5120, 13824, 3) == 0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the multi-GPU exchange at 8 ranks: host-side pointer arithmetic (never run on 8 GPUs by the builder)
+# ----------------------------------------------------------------------------------------------------------------
+class _FakeSP:
+    """SequenceParallel with the p2p exchange, minus torch.distributed: a fake table of per-rank arena base addresses
+    stands for the symmetric-memory rendezvous, the barrier is a no-op."""
+    exchange, p2p, fallback_reason, group = "p2p", True, None, None
+
+    def __init__(self, rank, world, L, D):
+        from realtime_video_b200.parallel import SequenceParallel
+        self.rank, self.world = rank, world
+        self.rows = lambda n: SequenceParallel.rows(self, n)
+        self.local_heads = lambda h: SequenceParallel.local_heads(self, h)
+        dh = D // world
+        self.arena = torch.zeros(4 * L * D + 4096, dtype=torch.bfloat16)
+        self.q_buf = self.arena[:L * dh].view(L, dh)
+        self.o_rows = self.arena[L * dh:L * dh + (L // world) * D].view(L // world, D)
+        self.o_heads = torch.zeros(L, dh, dtype=torch.bfloat16)
+        self.kv_off = L * dh + (L // world) * D
+        self.peer_base = [0x10_0000_0000 * (r + 1) for r in range(world)]
+        self.barriers = 0
+
+    def carve_kv(self, rows, dh):
+        n = rows * dh
+        k = self.arena[self.kv_off:self.kv_off + n].view(1, rows, dh // 128, 128)
+        v = self.arena[self.kv_off + n:self.kv_off + 2 * n].view(1, rows, dh // 128, 128)
+        return k, v
+
+    def exchange_buffers(self, L):
+        return self.q_buf[:L], self.o_heads[:L], self.o_rows[:L // self.world]
+
+    def peer_ptrs(self, t):
+        off = t.data_ptr() - self.arena.data_ptr()
+        assert 0 <= off < self.arena.numel() * 2, "tensor outside the symmetric arena"
+        return (ctypes.c_void_p * self.world)(*[b + off for b in self.peer_base])
+
+    def barrier(self):
+        self.barriers += 1
+
+    def gather_rows(self, x):
+        return x
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_p2p_exchange_pointer_arithmetic_up_to_8_ranks(on_recorder, world):
+    """Every rank of a `world`-way sequence-parallel run issues launches whose shard sizes, row offsets and PER-PEER
+    destination addresses are what the layout demands: rank r's rows land at row r*n of every peer's q buffer / K / V
+    slot (columns = the peer's heads), and the attention output of my heads goes back to row 0.. of the owners' row
+    buffers at my column block."""
+    from realtime_video_b200.dit import CausalWanModel
+    torch.manual_seed(1)
+    heads, D = 8, 1024
+    m = CausalWanModel(dim=D, ffn_dim=512, num_heads=heads, num_layers=1, text_dim=128).to(torch.bfloat16).eval()
+    blk = m.blocks[0]
+    blk.self_attn.fuse_projections()
+    fs_, frames = 64, 3
+    L = frames * fs_                   # 192 tokens
+    n_loc, dh = L // world, D // world
+    ca = {"k": torch.randn(1, 512, heads, 128).bfloat16(), "v": torch.randn(1, 512, heads, 128).bfloat16(), "is_init": True}
+    e0 = torch.randn(frames, 6, D).bfloat16()
+    for rank in range(world):
+        sp = _FakeSP(rank, world, L, D)
+        m.sp = sp
+        k, v = sp.carve_kv(2 * L, dh)
+        kv = {"k": k, "v": v, "global_end_index": L, "local_end_index": L}
+        x = torch.randn(n_loc, D).bfloat16()
+        on_recorder.kr_record_clear()
+        with torch.no_grad():
+            m._block(blk, x, e0, (frames, 8, 8), None, kv, ca, L, None)
+        calls = parse(on_recorder.kr_record_dump().decode())
+        m.sp = None
+        fns = [c["fn"] for c in calls]
+        assert fns == ["add_mod", "ln", "gemm", "qkv_post", "attn", "p2p_scatter_rows", "gemm", "ln", "gemm", "rmsnorm",
+                       "attn", "gemm", "ln", "gemm", "gemm"] and sp.barriers == 2
+        base = sp.arena.data_ptr()
+        ln, qkv, post, attn, scat, oproj = calls[1], calls[2], calls[3], calls[4], calls[5], calls[6]
+        assert ln["rows"] == n_loc and ln["row_offset"] == rank * n_loc and qkv["M"] == n_loc and qkv["N"] == 3 * D
+        assert post["rows"] == n_loc and post["row_offset"] == rank * n_loc and post["peer_cols"] == dh
+        assert post["ldqo"] == post["ldko"] == post["ldvo"] == dh and post["start_frame"] == L // fs_
+        k_slot_off = kv["k"][0].view(-1, dh)[L:].data_ptr() - base          # slot [L, 2L) of the local cache
+        v_slot_off = kv["v"][0].view(-1, dh)[L:].data_ptr() - base
+        for d in range(world):
+            pb = sp.peer_base[d]
+            assert post[f"qp{d}"] == pb + (sp.q_buf.data_ptr() - base) + rank * n_loc * dh * 2
+            assert post[f"kp{d}"] == pb + k_slot_off + rank * n_loc * dh * 2
+            assert post[f"vp{d}"] == pb + v_slot_off + rank * n_loc * dh * 2
+            assert scat[f"dp{d}"] == pb + (sp.o_rows.data_ptr() - base) + rank * dh * 2
+        for d in range(world, 8):
+            assert post[f"qp{d}"] == 0
+        assert attn["Lq"] == L and attn["Lkv"] == 2 * L and attn["heads"] == heads // world
+        assert attn["q"] == sp.q_buf.data_ptr() and attn["ldq"] == dh and attn["out"] == sp.o_heads.data_ptr()
+        assert scat["src"] == sp.o_heads.data_ptr() and scat["rows"] == L and scat["rows_per_peer"] == n_loc
+        assert scat["cols"] == dh and scat["ld_dst"] == D and scat["world"] == world
+        assert oproj["a"] == sp.o_rows.data_ptr() and oproj["M"] == n_loc and oproj["row_offset"] == rank * n_loc
+        assert (kv["global_end_index"], kv["local_end_index"]) == (2 * L, 2 * L)
